@@ -1,0 +1,73 @@
+"""ctypes binding of include/dkd_b200.h.  Fails loudly: there is no CPU or PyTorch fallback.
+
+The library is the product; PyTorch only owns device memory and streams.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdkd_b200.so")
+
+_P = c_void_p
+_I = c_int32
+_L = c_int64
+_F = c_float
+
+# name -> argument ctypes (return type is int unless listed in _RESTYPES)
+PROTOTYPES = {
+    "dkd_version": [],
+    "dkd_error_string": [_I],
+    "dkd_normalize_rows": [_P, _L, _I, _F, _P, _P, _L, _P],
+    "dkd_downsample_clips": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "dkd_build_proposals": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "dkd_score_max_f32": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P],
+    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P],
+    "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P],
+    "dkd_key_clip_dots": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "dkd_frame_attn_table": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "dkd_frame_fuse": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _L, _F, _F, _F, _I, _P, _P, _P],
+    "dkd_fuse_scores": [_P, _P, _F, _F, _P, _L, _P],
+    "dkd_topk": [_P, _I, _I, _L, _I, _I, _P, _P, _P],
+    "dkd_merge_topk": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "dkd_rank_of_gt": [_P, _I, _I, _L, _P, _P, _P, _P],
+    "dkd_candidates_to_csr": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "dkd_frame_fuse_csr": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P],
+    "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
+}
+_RESTYPES = {"dkd_error_string": c_char_p}
+
+_lib = None
+
+
+class DkdError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdkd_b200.so (built by build.py). Raises if it is missing — no fallback path exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DkdError(
+            f"{LIB_PATH} not found: build it with `python dl-dkd_b200/build.py` "
+            "(nvcc, sm_100a). dkd_b200 has no CPU / PyTorch fallback for the scoring path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int32)
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().dkd_error_string(code)
+        raise DkdError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)

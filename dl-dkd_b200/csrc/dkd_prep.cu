@@ -1,0 +1,354 @@
+// Corpus-side preparation kernels (query independent, run once per corpus / shard):
+// row normalisation + bf16 cast, clip downsample, clip-proposal builder, key-clip attention table.
+// All are HBM-bound streaming kernels; arithmetic is fp32.
+#include "dkd_common.cuh"
+
+namespace dkd {
+
+// ------------------------------------------------------------------------------------------
+// L2-normalise rows.  One warp per row, grid-stride.  F.normalize semantics
+// (method/model.py:318-319): x / max(||x||_2, eps) with a true division.
+__global__ void normalize_rows_kernel(const float* __restrict__ x, int64_t rows, int D, float eps,
+                                      float* __restrict__ of32, __nv_bfloat16* __restrict__ obf,
+                                      int64_t rows_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < rows_pad; r += nwarp) {
+    if (r >= rows) {  // zero padding rows
+      for (int d = lane; d < D; d += 32) {
+        if (of32) of32[r * D + d] = 0.f;
+        if (obf) obf[r * D + d] = __float2bfloat16(0.f);
+      }
+      continue;
+    }
+    const float* xr = x + r * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float v = xr[d];
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), eps);
+    for (int d = lane; d < D; d += 32) {
+      float v = __fdiv_rn(xr[d], denom);
+      if (of32) of32[r * D + d] = v;
+      if (obf) obf[r * D + d] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// average_to_fixed_length (method/data_provider.py:30-50) on the device.
+// idxs[i] = min(round_half_even(i / T * n), n - 1) in fp32; clip i = mean(frames[s:e]) or frames[s].
+__global__ void downsample_clips_kernel(const float* __restrict__ frames,
+                                        const int32_t* __restrict__ lengths, int L, int D, int T,
+                                        float* __restrict__ clips) {
+  const int n = blockIdx.x;
+  int len = lengths[n];
+  len = len < 1 ? 1 : (len > L ? L : len);
+  const float* f = frames + (int64_t)n * L * D;
+  float* c = clips + (int64_t)n * T * D;
+  for (int i = 0; i < T; ++i) {
+    // torch: arange(0, T+1, 1.0) / T * n, rounded half-to-even, clamped to n-1
+    float fs = __fmul_rn(__fdiv_rn((float)i, (float)T), (float)len);
+    float fe = __fmul_rn(__fdiv_rn((float)(i + 1), (float)T), (float)len);
+    int s = min((int)rintf(fs), len - 1);
+    int e = min((int)rintf(fe), len - 1);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v;
+      if (s < e) {
+        float acc = f[(int64_t)s * D + d];
+        for (int r = s + 1; r < e; ++r) acc = __fadd_rn(acc, f[(int64_t)r * D + d]);
+        v = __fdiv_rn(acc, (float)(e - s));
+      } else {
+        v = f[(int64_t)s * D + d];
+      }
+      c[(int64_t)i * D + d] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Clip-proposal builder.  One block per video, 16 warps; warp j owns window starts j and T-1-j
+// (balanced: T+1 windows per warp).  The T x D clip tile lives in shared memory (48 KB at
+// T=32, D=384); every window sum is a running fp32 sum over the window (the AvgPool1d order),
+// each lane holding D/32 features as bf16x2-friendly pairs.  Per window: one warp reduction
+// for the norm, one coalesced bf16 row store.
+template <int kPairs>  // D = 64 * kPairs
+__global__ void __launch_bounds__(512)
+build_proposals_kernel(const float* __restrict__ clips, int T, int D,
+                       __nv_bfloat16* __restrict__ prop_bf16, float* __restrict__ prop_scale,
+                       float* __restrict__ prop_f32) {
+  extern __shared__ float sclips[];  // T * D
+  const int n = blockIdx.x;
+  const int P = T * (T + 1) / 2;
+  const float* c = clips + (int64_t)n * T * D;
+  for (int i = threadIdx.x * 4; i < T * D; i += blockDim.x * 4) {
+    *reinterpret_cast<float4*>(&sclips[i]) = *reinterpret_cast<const float4*>(&c[i]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  // warp k owns starts k and T-1-k: T+1 windows per warp, balanced.
+  for (int sidx = warp; sidx < 2 * ((T + 1) / 2); sidx += nwarps) {
+    const int half = (T + 1) / 2;
+    const int s = (sidx < half) ? sidx : (T - 1 - (sidx - half));
+    if (sidx >= half && s == sidx - half) continue;  // odd T: middle start already done
+    float acc[2 * kPairs];
+#pragma unroll
+    for (int j = 0; j < 2 * kPairs; ++j) acc[j] = 0.f;
+    for (int w = 1; w <= T - s; ++w) {
+      const float* row = &sclips[(s + w - 1) * D];
+      float ss = 0.f;
+      float mean[2 * kPairs];
+      const float fw = (float)w;
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) {
+        float2 v = *reinterpret_cast<const float2*>(&row[64 * j + 2 * lane]);
+        acc[2 * j] = (w == 1) ? v.x : __fadd_rn(acc[2 * j], v.x);
+        acc[2 * j + 1] = (w == 1) ? v.y : __fadd_rn(acc[2 * j + 1], v.y);
+        mean[2 * j] = __fdiv_rn(acc[2 * j], fw);
+        mean[2 * j + 1] = __fdiv_rn(acc[2 * j + 1], fw);
+        ss = fmaf(mean[2 * j], mean[2 * j], ss);
+        ss = fmaf(mean[2 * j + 1], mean[2 * j + 1], ss);
+      }
+      ss = warp_sum(ss);
+      const float denom = fmaxf(sqrtf(ss), 1e-12f);
+      const int p = prop_index(w, s, T);
+      const int64_t ro = ((int64_t)n * P + p) * D;
+      if (prop_scale && lane == 0) prop_scale[(int64_t)n * P + p] = __fdiv_rn(1.0f, __fmul_rn(fw, denom));
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) {
+        if (prop_f32) {
+          *reinterpret_cast<float2*>(&prop_f32[ro + 64 * j + 2 * lane]) =
+              make_float2(mean[2 * j], mean[2 * j + 1]);
+        }
+        if (prop_bf16) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(__fdiv_rn(mean[2 * j], denom),
+                                                   __fdiv_rn(mean[2 * j + 1], denom));
+          *reinterpret_cast<__nv_bfloat162*>(&prop_bf16[ro + 64 * j + 2 * lane]) = b;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Key-clip attention table.  Block = (video n, chunk of kPC proposals), 256 threads.
+//  phase 1: logits[p][l] = (sum_{i in window p} E[n][l][i]) / w           (E tile in smem)
+//  phase 2: softmax over valid frames (one warp per proposal row, accurate expf)
+//  phase 3: g[p][:] = sum_l a[p][l] * val[n][l][:]  — val streamed through smem in 64-feature
+//           chunks, each thread keeps 3 proposals x 4 features x (D/64) chunks in registers
+//  phase 4: row norm (16-lane reduction), write fp32 and bf16 rows.
+constexpr int kPC = 48;   // proposals per block (528 = 11 * 48)
+constexpr int kLmax = 128;
+
+template <int kChunks>  // D = 64 * kChunks
+__global__ void __launch_bounds__(256)
+frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ val,
+                        const int32_t* __restrict__ lengths, int L, int T, int D,
+                        float* __restrict__ table_f32, __nv_bfloat16* __restrict__ table_bf16) {
+  extern __shared__ __align__(16) float smem_tab[];
+  float (*sV)[64] = reinterpret_cast<float (*)[64]>(smem_tab);                        // kLmax x 64
+  float (*sE)[33] = reinterpret_cast<float (*)[33]>(smem_tab + kLmax * 64);           // kLmax x 33
+  float (*sA)[kLmax + 1] = reinterpret_cast<float (*)[kLmax + 1]>(smem_tab + kLmax * 64 + kLmax * 33);
+  const int n = blockIdx.x;
+  const int P = T * (T + 1) / 2;
+  const int p0 = blockIdx.y * kPC;
+  int len = lengths[n];
+  len = len < 1 ? 1 : (len > L ? L : len);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < kLmax * 32; i += 256) {
+    int l = i >> 5, c = i & 31;
+    sE[l][c] = (l < L && c < T) ? E[((int64_t)n * L + l) * T + c] : 0.f;
+  }
+  __syncthreads();
+  // phase 1
+  for (int i = tid; i < kPC * kLmax; i += 256) {
+    const int pl = i / kLmax, l = i % kLmax;
+    const int p = p0 + pl;
+    float v = 0.f;
+    if (p < P && l < len) {
+      // invert p -> (w, s): windows of length w occupy [off_w, off_w + T - w + 1)
+      int w = 1, off = 0;
+      while (off + (T - w + 1) <= p) { off += T - w + 1; ++w; }
+      const int s = p - off;
+      float acc = sE[l][s];
+      for (int k = 1; k < w; ++k) acc = __fadd_rn(acc, sE[l][s + k]);
+      v = __fdiv_rn(acc, (float)w);
+    }
+    sA[pl][l] = v;
+  }
+  __syncthreads();
+  // phase 2
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int pl = warp; pl < kPC; pl += 8) {
+      float mx = -INFINITY;
+      for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sA[pl][l]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int l = lane; l < kLmax; l += 32) {
+        float e = (l < len) ? expf(sA[pl][l] - mx) : 0.f;
+        sA[pl][l] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      for (int l = lane; l < kLmax; l += 32) sA[pl][l] = __fdiv_rn(sA[pl][l], sum);
+    }
+  }
+  // phase 3
+  const int tp = tid >> 4;  // 0..15 -> proposals tp, tp+16, tp+32
+  const int td = tid & 15;  // float4 column
+  float acc[kChunks][3][4];
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[c][a][b] = 0.f;
+
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    __syncthreads();  // sA ready (first iter) / previous sV consumed
+    for (int i = tid; i < kLmax * 16; i += 256) {
+      const int l = i >> 4, q4 = i & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (l < len) v = *reinterpret_cast<const float4*>(&val[((int64_t)n * L + l) * D + c * 64 + q4 * 4]);
+      *reinterpret_cast<float4*>(&sV[l][q4 * 4]) = v;
+    }
+    __syncthreads();
+    for (int l = 0; l < len; ++l) {
+      const float4 v = *reinterpret_cast<const float4*>(&sV[l][td * 4]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float w = sA[tp + 16 * a][l];
+        acc[c][a][0] = fmaf(w, v.x, acc[c][a][0]);
+        acc[c][a][1] = fmaf(w, v.y, acc[c][a][1]);
+        acc[c][a][2] = fmaf(w, v.z, acc[c][a][2]);
+        acc[c][a][3] = fmaf(w, v.w, acc[c][a][3]);
+      }
+    }
+  }
+  // phase 4
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) ss = fmaf(acc[c][a][b], acc[c][a][b], ss);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    const int p = p0 + tp + 16 * a;
+    if (p < P) {
+      const int64_t ro = ((int64_t)n * P + p) * D;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        float4 o = make_float4(__fdiv_rn(acc[c][a][0], denom), __fdiv_rn(acc[c][a][1], denom),
+                               __fdiv_rn(acc[c][a][2], denom), __fdiv_rn(acc[c][a][3], denom));
+        if (table_f32) *reinterpret_cast<float4*>(&table_f32[ro + c * 64 + td * 4]) = o;
+        if (table_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(&table_bf16[ro + c * 64 + td * 4]) = pk;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dkd
+
+using namespace dkd;
+
+extern "C" int dkd_normalize_rows(const float* x, int64_t rows, int32_t D, float eps, float* out_f32,
+                                  uint16_t* out_bf16, int64_t rows_out_pad, void* stream) {
+  if (!x || rows < 0 || D <= 0 || (!out_f32 && !out_bf16)) return DKD_ERR_ARG;
+  if (rows_out_pad < rows) rows_out_pad = rows;
+  if (rows_out_pad == 0) return DKD_OK;
+  const int wpb = 8;
+  int64_t blocks = (rows_out_pad + wpb - 1) / wpb;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  normalize_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows_out_pad);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_downsample_clips(const float* frames, const int32_t* lengths, int32_t Nv, int32_t L,
+                                    int32_t D, int32_t T, float* clips, void* stream) {
+  if (!frames || !lengths || !clips || Nv < 0 || L <= 0 || D <= 0 || T <= 0) return DKD_ERR_ARG;
+  if (Nv == 0) return DKD_OK;
+  downsample_clips_kernel<<<Nv, 128, 0, (cudaStream_t)stream>>>(frames, lengths, L, D, T, clips);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+template <int kPairs>
+static int launch_build_proposals(const float* clips, int Nv, int T, int D, uint16_t* pb, float* ps,
+                                  float* pf, cudaStream_t st) {
+  size_t smem = (size_t)T * D * sizeof(float);
+  DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  build_proposals_kernel<kPairs><<<Nv, 512, smem, st>>>(clips, T, D, reinterpret_cast<__nv_bfloat16*>(pb), ps, pf);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_build_proposals(const float* clips, int32_t Nv, int32_t T, int32_t D,
+                                   uint16_t* prop_bf16, float* prop_scale, float* prop_f32,
+                                   void* stream) {
+  if (!clips || Nv < 0 || T <= 0 || D <= 0) return DKD_ERR_ARG;
+  if (T > 32 || D % 64 != 0 || D > 512) return DKD_ERR_SHAPE;
+  if (Nv == 0) return DKD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D / 64) {
+    case 1: return launch_build_proposals<1>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 2: return launch_build_proposals<2>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 3: return launch_build_proposals<3>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 4: return launch_build_proposals<4>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 5: return launch_build_proposals<5>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 6: return launch_build_proposals<6>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 7: return launch_build_proposals<7>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 8: return launch_build_proposals<8>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+  }
+  return DKD_ERR_SHAPE;
+}
+
+template <int kChunks>
+static int launch_frame_table(const float* E, const float* val, const int32_t* lengths, int Nv, int L,
+                              int T, int D, float* tf, uint16_t* tb, cudaStream_t st) {
+  const int P = T * (T + 1) / 2;
+  dim3 grid(Nv, (P + kPC - 1) / kPC);
+  const size_t smem = sizeof(float) * (kLmax * 64 + kLmax * 33 + kPC * (kLmax + 1));
+  DKD_CUDA_TRY(cudaFuncSetAttribute(frame_attn_table_kernel<kChunks>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  frame_attn_table_kernel<kChunks><<<grid, 256, smem, st>>>(E, val, lengths, L, T, D, tf,
+                                                            reinterpret_cast<__nv_bfloat16*>(tb));
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_frame_attn_table(const float* E, const float* val, const int32_t* lengths, int32_t Nv,
+                                    int32_t L, int32_t T, int32_t D, float* table_f32,
+                                    uint16_t* table_bf16, void* stream) {
+  if (!E || !val || !lengths || Nv < 0 || (!table_f32 && !table_bf16)) return DKD_ERR_ARG;
+  if (L <= 0 || L > kLmax || T <= 0 || T > 32 || D % 64 != 0 || D > 512) return DKD_ERR_SHAPE;
+  if (Nv == 0) return DKD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D / 64) {
+    case 1: return launch_frame_table<1>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 2: return launch_frame_table<2>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 3: return launch_frame_table<3>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 4: return launch_frame_table<4>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 6: return launch_frame_table<6>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 8: return launch_frame_table<8>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+  }
+  return DKD_ERR_SHAPE;
+}

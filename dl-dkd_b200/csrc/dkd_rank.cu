@@ -1,0 +1,289 @@
+// Ranking kernels: warp-level streaming top-K selection, multi-shard merge, rank-of-GT,
+// candidate CSR inversion and candidate sort.  Replace the host np.argsort of
+// eval_q2m (method/eval.py:59-94): only the top-100 and the GT rank matter for R@K / medr / meanr.
+//
+// Order everywhere: score descending, video id ascending on equal scores — encoded as one
+// 64-bit key (monotone float bits << 32 | ~id) so that "better" is a plain integer compare.
+#include "dkd_common.cuh"
+
+namespace dkd {
+
+typedef unsigned long long u64;
+
+// Bitonic sort (descending) of S (power of two) keys in shared memory by one warp.
+__device__ __forceinline__ void warp_bitonic_desc(u64* a, int S, int lane) {
+  for (int k = 2; k <= S; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (S >> 1); t += 32) {
+        // t-th compare-exchange pair of this stage
+        const int i = ((t / j) * (j << 1)) + (t % j);
+        const int l = i + j;
+        const bool desc = ((i & k) == 0);
+        const u64 x = a[i], y = a[l];
+        const bool swap = desc ? (x < y) : (x > y);
+        if (swap) { a[i] = y; a[l] = x; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Streaming top-K by one warp: `list` = first K slots (sorted desc), queue = slots [K, S).
+struct WarpSelect {
+  u64* buf;   // S slots
+  int S, K, lane;
+  int qn;     // queued (warp-uniform)
+  u64 thresh; // K-th best so far (warp-uniform)
+  __device__ void init(u64* b, int S_, int K_, int lane_) {
+    buf = b; S = S_; K = K_; lane = lane_; qn = 0; thresh = 0ull;
+    for (int i = lane; i < S; i += 32) buf[i] = 0ull;
+    __syncwarp();
+  }
+  __device__ void flush() {
+    warp_bitonic_desc(buf, S, lane);
+    for (int i = K + lane; i < S; i += 32) buf[i] = 0ull;
+    __syncwarp();
+    thresh = buf[K - 1];
+    qn = 0;
+  }
+  // all 32 lanes call; `valid` lanes offer `key`
+  __device__ void push(u64 key, bool valid) {
+    const bool take = valid && key > thresh;
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (bal == 0u) return;
+    if (take) buf[K + qn + __popc(bal & ((1u << lane) - 1u))] = key;
+    qn += __popc(bal);
+    __syncwarp();
+    if (K + qn + 32 > S) flush();
+  }
+};
+
+// scores (M, Nv) dense, implicit ids id_base + n.
+__global__ void topk_dense_kernel(const float* __restrict__ scores, int M, int Nv, int64_t ld, int K, int S,
+                                  int id_base, float* __restrict__ out_scores, int32_t* __restrict__ out_ids) {
+  extern __shared__ __align__(8) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  WarpSelect ws;
+  ws.init(reinterpret_cast<u64*>(smem_raw) + (size_t)warp * S, S, K, lane);
+  const float* row = scores + (int64_t)m * ld;
+  for (int n0 = 0; n0 < Nv; n0 += 32) {
+    const int n = n0 + lane;
+    const bool valid = n < Nv;
+    const float s = valid ? row[n] : 0.f;
+    ws.push(pack_key(s, id_base + n), valid);
+  }
+  ws.flush();
+  for (int j = lane; j < K; j += 32) {
+    const u64 k = ws.buf[j];
+    out_scores[(int64_t)m * K + j] = k ? key_score(k) : -INFINITY;
+    out_ids[(int64_t)m * K + j] = k ? key_id(k) : -1;
+  }
+}
+
+// (G, M, K) shard lists -> (M, K).  Entries with id < 0 are padding.
+__global__ void merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids, int G,
+                                  int M, int K, int S, float* __restrict__ out_scores,
+                                  int32_t* __restrict__ out_ids) {
+  extern __shared__ __align__(8) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  WarpSelect ws;
+  ws.init(reinterpret_cast<u64*>(smem_raw) + (size_t)warp * S, S, K, lane);
+  for (int g = 0; g < G; ++g) {
+    const int64_t base = ((int64_t)g * M + m) * K;
+    for (int j0 = 0; j0 < K; j0 += 32) {
+      const int j = j0 + lane;
+      bool valid = j < K;
+      int id = valid ? ids[base + j] : -1;
+      valid = valid && id >= 0;
+      const float s = valid ? scores[base + j] : 0.f;
+      ws.push(pack_key(s, id), valid);
+    }
+  }
+  ws.flush();
+  for (int j = lane; j < K; j += 32) {
+    const u64 k = ws.buf[j];
+    out_scores[(int64_t)m * K + j] = k ? key_score(k) : -INFINITY;
+    out_ids[(int64_t)m * K + j] = k ? key_id(k) : -1;
+  }
+}
+
+// Sort K candidates per query, keep K_out.
+__global__ void sort_candidates_kernel(const float* __restrict__ cs, const int32_t* __restrict__ cid, int M,
+                                       int K, int K_out, int S, float* __restrict__ out_scores,
+                                       int32_t* __restrict__ out_ids) {
+  extern __shared__ __align__(8) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  u64* buf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * S;
+  for (int j = lane; j < S; j += 32) {
+    u64 k = 0ull;
+    if (j < K) {
+      const int id = cid[(int64_t)m * K + j];
+      if (id >= 0) k = pack_key(cs[(int64_t)m * K + j], id);
+    }
+    buf[j] = k;
+  }
+  __syncwarp();
+  warp_bitonic_desc(buf, S, lane);
+  for (int j = lane; j < K_out; j += 32) {
+    const u64 k = buf[j];
+    out_scores[(int64_t)m * K_out + j] = k ? key_score(k) : -INFINITY;
+    out_ids[(int64_t)m * K_out + j] = k ? key_id(k) : -1;
+  }
+}
+
+// rank of the best GT video: one warp per query.
+__global__ void rank_of_gt_kernel(const float* __restrict__ scores, int M, int Nv, int64_t ld,
+                                  const int32_t* __restrict__ gt_ptr, const int32_t* __restrict__ gt_ids,
+                                  int32_t* __restrict__ out_rank) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  const float* row = scores + (int64_t)m * ld;
+  int best = Nv + 1;
+  for (int g = gt_ptr[m]; g < gt_ptr[m + 1]; ++g) {
+    const int gt = gt_ids[g];
+    if (gt < 0 || gt >= Nv) continue;
+    const float sg = row[gt];
+    int cnt = 0;
+    for (int n = lane; n < Nv; n += 32) {
+      const float s = row[n];
+      cnt += (s > sg) || (s == sg && n < gt);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    best = min(best, cnt + 1);
+  }
+  if (lane == 0) out_rank[m] = best;
+}
+
+__global__ void cand_hist_kernel(const int32_t* __restrict__ cand, int64_t total, int Nv, int id_base,
+                                 int32_t* __restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = cand[i] - id_base;
+    if (n >= 0 && n < Nv) atomicAdd(&counts[n], 1);
+  }
+}
+// single block exclusive scan: counts[0..Nv) -> vid_ptr[0..Nv]; counts reset to 0 (reused as cursors)
+__global__ void cand_scan_kernel(int32_t* __restrict__ counts, int Nv, int32_t* __restrict__ vid_ptr) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x;
+  const int per = (Nv + 1023) / 1024;
+  const int b = tid * per, e = min(b + per, Nv);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) { int t = part[i]; part[i] = run; run += t; }
+    vid_ptr[Nv] = run;
+  }
+  __syncthreads();
+  int run = part[tid];
+  for (int i = b; i < e; ++i) {
+    const int c = counts[i];
+    vid_ptr[i] = run;
+    run += c;
+    counts[i] = 0;
+  }
+}
+__global__ void cand_fill_kernel(const int32_t* __restrict__ cand, int64_t total, int K, int Nv, int id_base,
+                                 int32_t* __restrict__ cursors, const int32_t* __restrict__ vid_ptr,
+                                 int32_t* __restrict__ q_list, int32_t* __restrict__ slot) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = cand[i] - id_base;
+    if (n >= 0 && n < Nv) {
+      const int e = vid_ptr[n] + atomicAdd(&cursors[n], 1);
+      q_list[e] = (int)(i / K);
+      slot[e] = (int)i;
+    }
+  }
+}
+
+}  // namespace dkd
+
+using namespace dkd;
+
+static int pow2_at_least(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+extern "C" int dkd_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, int32_t K, int32_t id_base,
+                        float* out_scores, int32_t* out_ids, void* stream) {
+  if (!scores || !out_scores || !out_ids || M < 0 || Nv < 0 || ld < Nv) return DKD_ERR_ARG;
+  if (K <= 0 || K > 256) return DKD_ERR_SHAPE;
+  if (M == 0) return DKD_OK;
+  const int S = 2 * pow2_at_least(K);
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * S * sizeof(u64);
+  topk_dense_kernel<<<(M + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(
+      scores, M, Nv, ld, K, S, id_base, out_scores, out_ids);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_merge_topk(const float* scores, const int32_t* ids, int32_t G, int32_t M, int32_t K,
+                              float* out_scores, int32_t* out_ids, void* stream) {
+  if (!scores || !ids || !out_scores || !out_ids || G <= 0 || M < 0) return DKD_ERR_ARG;
+  if (K <= 0 || K > 256) return DKD_ERR_SHAPE;
+  if (M == 0) return DKD_OK;
+  const int S = 2 * pow2_at_least(K);
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * S * sizeof(u64);
+  merge_topk_kernel<<<(M + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(scores, ids, G, M, K, S,
+                                                                                 out_scores, out_ids);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_sort_candidates(const float* cand_scores, const int32_t* cand_ids, int32_t M, int32_t K,
+                                   int32_t K_out, float* out_scores, int32_t* out_ids, void* stream) {
+  if (!cand_scores || !cand_ids || !out_scores || !out_ids || M < 0) return DKD_ERR_ARG;
+  if (K <= 0 || K > 512 || K_out <= 0 || K_out > K) return DKD_ERR_SHAPE;
+  if (M == 0) return DKD_OK;
+  const int S = pow2_at_least(K);
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * S * sizeof(u64);
+  sort_candidates_kernel<<<(M + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(
+      cand_scores, cand_ids, M, K, K_out, S, out_scores, out_ids);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_rank_of_gt(const float* scores, int32_t M, int32_t Nv, int64_t ld, const int32_t* gt_ptr,
+                              const int32_t* gt_ids, int32_t* out_rank, void* stream) {
+  if (!scores || !gt_ptr || !gt_ids || !out_rank || M < 0 || Nv < 0 || ld < Nv) return DKD_ERR_ARG;
+  if (M == 0) return DKD_OK;
+  const int wpb = 8;
+  rank_of_gt_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(scores, M, Nv, ld, gt_ptr,
+                                                                              gt_ids, out_rank);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_candidates_to_csr(const int32_t* cand_ids, int32_t M, int32_t K, int32_t Nv,
+                                     int32_t id_base, int32_t* counts, int32_t* vid_ptr, int32_t* q_list,
+                                     int32_t* slot, void* stream) {
+  if (!cand_ids || !counts || !vid_ptr || !q_list || !slot || M < 0 || K <= 0 || Nv <= 0) return DKD_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)M * K;
+  DKD_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)Nv, st));
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  cand_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand_ids, total, Nv, id_base, counts);
+  DKD_LAUNCH_CHECK();
+  cand_scan_kernel<<<1, 1024, 0, st>>>(counts, Nv, vid_ptr);
+  DKD_LAUNCH_CHECK();
+  cand_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand_ids, total, K, Nv, id_base, counts, vid_ptr, q_list, slot);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}

@@ -1,0 +1,401 @@
+// bf16 scoring GEMM on tcgen05 tensor cores with a fused max/argmax-over-rows epilogue.
+//
+//   S[m, (n, r)] = q_bf16[m] . x_bf16[n * R + r]           fp32 accumulate in TMEM
+//   out_max[m, n] = max_r S,  out_arg[m, n] = first argmax_r   (masked rows = -1e10)
+//
+// R = L (frame path, method/model.py:318-327) or R = P = 528 clip proposals.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0  : TMA producer for the corpus (B) ring — BLOCK_N rows x 64 features per stage
+//   warp 1  : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warp 2  : TMA producer for the query tile (A: 128 queries x D, resident for a whole work
+//             item) + TMEM allocation
+//   warp 3  : spare
+//   warps 4-7: epilogue — tcgen05.ld 32x32b, running (max, first-argmax) per query row across
+//             the R / BLOCK_N tiles of one video, direct fp32 / int32 stores.
+// A work item = (query tile of 128, chunk of kVideoChunk videos); items are ordered query-tile
+// fastest so that CTAs running at the same time stream the same corpus rows out of L2.
+//
+// Operand layout: K-major, 128-byte swizzle (TMA SWIZZLE_128B <-> UMMA SWIZZLE_128B descriptors),
+// one K block = 64 bf16 = 128 B per row, 8-row groups 1024 B apart.
+#include <cuda.h>  // CUtensorMap types only; the encode entry point is fetched at run time
+#include <cstdio>
+
+#include "dkd_common.cuh"
+
+namespace dkd {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxKBlocks = 8;    // D <= 512
+constexpr int kMaxStages = 8;
+constexpr int kNumThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {
+      printf("dkd_score_max_bf16: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (sm_100 version 1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // layout: SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n.
+__host__ __device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+struct GemmParams {
+  int M, Mpad, Nv, R, D;
+  int block_n;        // columns per MMA tile; R % block_n == 0
+  int stages;         // B ring depth
+  int video_chunk;    // videos per work item
+  const uint8_t* mask;
+  float* out_max;
+  int32_t* out_arg;
+  int64_t ld_out;
+};
+
+struct __align__(8) SmemCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t a_full, a_empty;
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool kHasMask>
+__global__ void __launch_bounds__(kNumThreads, 1)
+score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                      const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int num_kb = p.D / kBlockK;
+  const uint32_t a_kb_bytes = kBlockM * kBlockK * 2;        // 16 KB per K block
+  const uint32_t b_stage_bytes = p.block_n * kBlockK * 2;   // block_n x 128 B
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)num_kb * a_kb_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_b + (size_t)p.stages * b_stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_video = p.R / p.block_n;
+  const int num_q_tiles = p.Mpad / kBlockM;
+  const int num_vchunks = (p.Nv + p.video_chunk - 1) / p.video_chunk;
+  const int num_items = num_q_tiles * num_vchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    mbar_init(&ctl->a_full, 1);
+    mbar_init(&ctl->a_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_x); }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===== corpus (B) producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int vchunk = item / num_q_tiles;
+        const int v0 = vchunk * p.video_chunk;
+        const int v1 = min(v0 + p.video_chunk, p.Nv);
+        for (int v = v0; v < v1; ++v) {
+          for (int t = 0; t < tiles_per_video; ++t) {
+            const int row = v * p.R + t * p.block_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              mbar_wait(&ctl->empty[stage], phase ^ 1);
+              mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
+              tma_load_2d(&map_x, &ctl->full[stage], smem_b + (size_t)stage * b_stage_bytes, kb * kBlockK, row);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== query tile (A) producer =====
+    if (lane == 0) {
+      uint32_t iphase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int q_tile = item % num_q_tiles;
+        mbar_wait(&ctl->a_empty, iphase ^ 1);
+        mbar_expect_tx(&ctl->a_full, (uint32_t)num_kb * a_kb_bytes);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(&map_q, &ctl->a_full, smem_a + (size_t)kb * a_kb_bytes, kb * kBlockK, q_tile * kBlockM);
+        iphase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.block_n);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t iphase = 0;
+      uint32_t tile_ctr = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int vchunk = item / num_q_tiles;
+        const int v0 = vchunk * p.video_chunk;
+        const int v1 = min(v0 + p.video_chunk, p.Nv);
+        mbar_wait(&ctl->a_full, iphase);
+        iphase ^= 1;
+        tc_fence_after();
+        const int ntiles = (v1 - v0) * tiles_per_video;
+        for (int tl = 0; tl < ntiles; ++tl, ++tile_ctr) {
+          const uint32_t as = tile_ctr & 1u;
+          const uint32_t aphase = (tile_ctr >> 1) & 1u;
+          mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)kb * a_kb_bytes));
+            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)stage * b_stage_bytes));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in 16-byte units
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&ctl->empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&ctl->tmem_full[as]);
+        }
+        umma_commit(&ctl->a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t tile_ctr = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int q_tile = item % num_q_tiles;
+      const int vchunk = item / num_q_tiles;
+      const int v0 = vchunk * p.video_chunk;
+      const int v1 = min(v0 + p.video_chunk, p.Nv);
+      const int m = q_tile * kBlockM + row_in_tile;
+      for (int v = v0; v < v1; ++v) {
+        float best = -INFINITY;
+        int besti = 0;
+        for (int t = 0; t < tiles_per_video; ++t, ++tile_ctr) {
+          const uint32_t as = tile_ctr & 1u;
+          const uint32_t aphase = (tile_ctr >> 1) & 1u;
+          mbar_wait(&ctl->tmem_full[as], aphase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)p.block_n;
+          for (int c = 0; c < p.block_n; c += 16) {
+            float vals[16];
+            tmem_ld16(taddr + (uint32_t)c, vals);
+            const int col0 = t * p.block_n + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float s = vals[j];
+              if (kHasMask) {
+                if (__ldg(&p.mask[(int64_t)v * p.R + col0 + j]) == 0) s = DKD_MASKED_SCORE;
+              }
+              if (s > best) { best = s; besti = col0 + j; }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&ctl->tmem_empty[as]);
+        }
+        if (m < p.M) {
+          p.out_max[(int64_t)m * p.ld_out + v] = best;
+          if (p.out_arg) p.out_arg[(int64_t)m * p.ld_out + v] = besti;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return DKD_ERR_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DKD_OK : DKD_ERR_DRIVER;
+}
+
+// Largest multiple of 16 that divides R and is <= 256.
+static int pick_block_n(int R) {
+  for (int n = 256; n >= 16; n -= 16)
+    if (R % n == 0) return n;
+  return 0;
+}
+
+}  // namespace dkd
+
+using namespace dkd;
+
+extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
+                                  int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                                  int32_t* out_arg, int64_t ld_out, void* stream) {
+  if (!q_bf16 || !x_bf16 || !out_max || M < 0 || Nv < 0 || ld_out < Nv) return DKD_ERR_ARG;
+  if (Mpad < M || Mpad % kBlockM != 0) return DKD_ERR_SHAPE;
+  if (R <= 0 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(x_bf16) & 15)) return DKD_ERR_ALIGN;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  if ((int64_t)Nv * R > 0x7fffffffLL) return DKD_ERR_SHAPE;
+  const int block_n = pick_block_n(R);
+  if (block_n == 0) return DKD_ERR_SHAPE;
+
+  int dev = 0, sms = 0, max_smem = 0;
+  DKD_CUDA_TRY(cudaGetDevice(&dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+  const int num_kb = D / kBlockK;
+  const size_t a_bytes = (size_t)num_kb * kBlockM * kBlockK * 2;
+  const size_t b_stage = (size_t)block_n * kBlockK * 2;
+  const size_t fixed = a_bytes + sizeof(SmemCtl) + 1024 /* alignment slack */ + 256;
+  if ((size_t)max_smem < fixed + 2 * b_stage) return DKD_ERR_SHAPE;
+  int stages = (int)(((size_t)max_smem - fixed) / b_stage);
+  if (stages > kMaxStages) stages = kMaxStages;
+  const size_t smem_bytes = fixed + (size_t)stages * b_stage;
+
+  CUtensorMap map_q, map_x;
+  int rc = make_map_2d(&map_q, q_bf16, (uint64_t)Mpad, (uint64_t)D, kBlockM);
+  if (rc) return rc;
+  rc = make_map_2d(&map_x, x_bf16, (uint64_t)Nv * R, (uint64_t)D, (uint32_t)block_n);
+  if (rc) return rc;
+
+  GemmParams p{};
+  p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages;
+  p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
+  // videos per work item: enough items for ~all SMs x many waves, >= 1
+  const int num_q_tiles = Mpad / kBlockM;
+  int vc = 16;
+  while (vc > 1 && (int64_t)num_q_tiles * ((Nv + vc - 1) / vc) < (int64_t)sms * 8) vc >>= 1;
+  p.video_chunk = vc;
+  const int64_t num_items = (int64_t)num_q_tiles * ((Nv + vc - 1) / vc);
+  const int grid = (int)(num_items < sms ? num_items : sms);
+
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask) {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(score_max_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    score_max_bf16_kernel<true><<<grid, kNumThreads, smem_bytes, st>>>(map_q, map_x, p);
+  } else {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(score_max_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    score_max_bf16_kernel<false><<<grid, kNumThreads, smem_bytes, st>>>(map_q, map_x, p);
+  }
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}

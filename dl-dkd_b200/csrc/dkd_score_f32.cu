@@ -1,0 +1,418 @@
+// Exact fp32 (SIMT) scoring kernels: the fp32 flavour of get_sim_scores (method/model.py:307-329)
+// and of the clip-scale head, used (a) as the exact drop-in path, (b) to rescore the bf16 GEMM's
+// top-K candidates, (c) for the key-clip dot products of the attention table.
+//
+// One tiled "dots" kernel: block = 64 query rows x kRows corpus rows of ONE video, K = D streamed
+// in 32-wide chunks through shared memory (padded stride 36 words: conflict-free LDS.128),
+// 256 threads, each thread 2 query rows x kRows/8 corpus rows.  Three epilogues.
+#include "dkd_common.cuh"
+
+namespace dkd {
+
+constexpr int kTM = 64;      // query rows per block
+constexpr int kKC = 32;      // K chunk
+constexpr int kLd = kKC + 4; // padded smem stride (words); 36 % 32 == 4 -> 8 rows hit 32 banks
+
+enum { EPI_MAX = 0, EPI_CLIP = 1, EPI_STORE = 2 };
+
+struct DotsParams {
+  const float* q;          // query rows
+  int64_t q_video_stride;  // elements added per video (0: queries shared by all videos)
+  int M;                   // number of query rows (dense) / upper bound (CSR)
+  const float* x;          // (Nv, R, D)
+  int R, D, T;
+  const uint8_t* mask;     // (Nv, R) or null
+  const float* scale;      // (Nv, P) EPI_CLIP
+  float* out_max;
+  int32_t* out_arg;
+  int64_t ld_out;
+  float* out_rows;         // EPI_MAX optional (M, R, Nv); EPI_STORE: E (Nv, M, T)
+  int Nv;
+  const int32_t* vid_ptr;  // CSR (optional)
+  const int32_t* q_list;
+};
+
+template <int kRows, int kEpi>
+__global__ void __launch_bounds__(256)
+dots_kernel(const DotsParams p) {
+  constexpr int kJ = kRows / 8;
+  __shared__ __align__(16) float sQ[kTM * kLd];
+  __shared__ __align__(16) float sX[kRows * kLd];
+  __shared__ float sScale[(kEpi == EPI_CLIP) ? 528 : 1];
+  __shared__ float sDots[(kEpi == EPI_CLIP) ? kTM * 33 : 1];
+
+  const int n = blockIdx.x;
+  const int tile = blockIdx.y;
+  int e0 = 0, count = p.M;
+  if (p.vid_ptr) {
+    e0 = p.vid_ptr[n];
+    count = p.vid_ptr[n + 1] - e0;
+  }
+  const int r0 = tile * kTM;
+  if (r0 >= count) return;
+  const int tid = threadIdx.x;
+  const int tm = tid >> 3;  // 0..31 -> query rows tm, tm + 32
+  const int ti = tid & 7;   // corpus rows ti + 8 j
+  const float* qbase = p.q + (int64_t)n * p.q_video_stride;
+  const float* xbase = p.x + (int64_t)n * p.R * p.D;
+
+  float acc[2][kJ];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) acc[a][j] = 0.f;
+
+  // global row of each of the 2 float4 slots this thread loads for the Q tile
+  // Q tile: 64 rows x 8 float4 = 512 float4 -> 2 per thread
+  int64_t qrow[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r = (tid + t * 256) >> 3;
+    const int lr = r0 + r;
+    if (lr < count) qrow[t] = p.q_list ? (int64_t)p.q_list[e0 + lr] : (int64_t)lr;
+    else qrow[t] = -1;
+  }
+
+  for (int kc = 0; kc < p.D; kc += kKC) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int idx = tid + t * 256;
+      const int r = idx >> 3, c4 = idx & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qrow[t] >= 0) v = *reinterpret_cast<const float4*>(&qbase[qrow[t] * p.D + kc + c4 * 4]);
+      *reinterpret_cast<float4*>(&sQ[r * kLd + c4 * 4]) = v;
+    }
+#pragma unroll
+    for (int t = 0; t < kRows / 32; ++t) {
+      const int idx = tid + t * 256;
+      const int r = idx >> 3, c4 = idx & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.R) v = *reinterpret_cast<const float4*>(&xbase[(int64_t)r * p.D + kc + c4 * 4]);
+      *reinterpret_cast<float4*>(&sX[r * kLd + c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kKC; k += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sQ[tm * kLd + k]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sQ[(tm + 32) * kLd + k]);
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(&sX[(ti + 8 * j) * kLd + k]);
+        acc[0][j] = fmaf(a0.x, b.x, acc[0][j]);
+        acc[0][j] = fmaf(a0.y, b.y, acc[0][j]);
+        acc[0][j] = fmaf(a0.z, b.z, acc[0][j]);
+        acc[0][j] = fmaf(a0.w, b.w, acc[0][j]);
+        acc[1][j] = fmaf(a1.x, b.x, acc[1][j]);
+        acc[1][j] = fmaf(a1.y, b.y, acc[1][j]);
+        acc[1][j] = fmaf(a1.z, b.z, acc[1][j]);
+        acc[1][j] = fmaf(a1.w, b.w, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+
+  if constexpr (kEpi == EPI_STORE) {
+    // E[n][m][row] = key[n][m] . clips[n][row]
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int lr = r0 + tm + 32 * a;
+      if (lr >= count) continue;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int row = ti + 8 * j;
+        if (row < p.T) p.out_rows[((int64_t)n * p.M + lr) * p.T + row] = acc[a][j];
+      }
+    }
+  } else if constexpr (kEpi == EPI_MAX) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int lr = r0 + tm + 32 * a;
+      const bool live = lr < count;
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int row = ti + 8 * j;
+        if (row < p.R) {
+          float v = acc[a][j];
+          if (p.mask && p.mask[(int64_t)n * p.R + row] == 0) v = DKD_MASKED_SCORE;
+          if (live && p.out_rows) {
+            const int64_t m = p.q_list ? p.q_list[e0 + lr] : lr;
+            p.out_rows[(m * p.R + row) * (int64_t)p.Nv + n] = v;
+          }
+          if (better(v, row, bv, bi)) { bv = v; bi = row; }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (live && ti == 0) {
+        const int64_t o = p.vid_ptr ? (int64_t)(e0 + lr) : (int64_t)lr * p.ld_out + n;
+        p.out_max[o] = bv;
+        if (p.out_arg) p.out_arg[o] = bi;
+      }
+    }
+  } else {  // EPI_CLIP: window sums of per-clip dots x prop_scale, max / first argmax over proposals
+    const int T = p.T, P = T * (T + 1) / 2;
+    for (int i = tid; i < P; i += 256) sScale[i] = p.scale[(int64_t)n * P + i];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) sDots[(tm + 32 * a) * 33 + ti + 8 * j] = acc[a][j];
+    __syncthreads();
+    const int m = tid >> 2, sub = tid & 3;  // 4 threads per query row, starts s = sub, sub+4, ...
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = sub; s < T; s += 4) {
+      float run = 0.f;
+      for (int w = 1; w <= T - s; ++w) {
+        const float d = sDots[m * 33 + s + w - 1];
+        run = (w == 1) ? d : __fadd_rn(run, d);
+        const int pi = prop_index(w, s, T);
+        const float v = __fmul_rn(run, sScale[pi]);
+        if (better(v, pi, bv, bi)) { bv = v; bi = pi; }
+      }
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    const int lr = r0 + m;
+    if (lr < count && sub == 0) {
+      const int64_t o = p.vid_ptr ? (int64_t)(e0 + lr) : (int64_t)lr * p.ld_out + n;
+      p.out_max[o] = bv;
+      if (p.out_arg) p.out_arg[o] = bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Frame-scale score + branch fusion.  8 lanes per (query, video) pair; block = 256 threads
+// covers 32 queries x 8 videos; grid x = query tiles (fastest) so concurrent blocks share the
+// same 8 videos' table slices in L2.
+template <typename TT>
+struct RowLoader;
+template <>
+struct RowLoader<float> {
+  static __device__ __forceinline__ float dot(const float* a, const float* b, int D, int sub) {
+    float acc = 0.f;
+    for (int d = sub * 4; d < D; d += 32) {
+      const float4 x = *reinterpret_cast<const float4*>(a + d);
+      const float4 y = *reinterpret_cast<const float4*>(b + d);
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+      acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    return acc;
+  }
+};
+template <>
+struct RowLoader<__nv_bfloat16> {
+  static __device__ __forceinline__ float dot(const __nv_bfloat16* a, const __nv_bfloat16* b, int D, int sub) {
+    float acc = 0.f;
+    for (int d = sub * 8; d < D; d += 64) {
+      const uint4 x = *reinterpret_cast<const uint4*>(a + d);
+      const uint4 y = *reinterpret_cast<const uint4*>(b + d);
+      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
+        acc = fmaf(xf.x, yf.x, acc);
+        acc = fmaf(xf.y, yf.y, acc);
+      }
+    }
+    return acc;
+  }
+};
+
+__device__ __forceinline__ float fuse_branch(float clip, float frame, float wc, float wf, float wb) {
+  // torch: w_clip * clip + w_frame * frame ; numpy: w_branch * branch   (no FMA contraction)
+  const float br = __fadd_rn(__fmul_rn(wc, clip), __fmul_rn(wf, frame));
+  return __fmul_rn(wb, br);
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(256)
+frame_fuse_kernel(const TT* __restrict__ q, const TT* __restrict__ table,
+                  const float* __restrict__ clip, const int32_t* __restrict__ key_clip, int M, int Nv,
+                  int P, int D, int64_t ld, float wc, float wf, float wb, int accumulate,
+                  float* __restrict__ out_frame, float* __restrict__ fused) {
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int n = blockIdx.y * 8 + (grp & 7);
+  const int mrow = grp >> 3;  // 0..3
+  for (int it = 0; it < 8; ++it) {
+    const int m = blockIdx.x * 32 + it * 4 + mrow;
+    const bool live = (m < M) && (n < Nv);
+    float acc = 0.f;
+    int64_t o = 0;
+    if (live) {
+      o = (int64_t)m * ld + n;
+      int k = key_clip[o];
+      k = k < 0 ? 0 : (k >= P ? P - 1 : k);
+      acc = RowLoader<TT>::dot(q + (int64_t)m * D, table + ((int64_t)n * P + k) * D, D, sub);
+    }
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (live && sub == 0) {
+      if (out_frame) out_frame[o] = acc;
+      if (fused) {
+        const float v = fuse_branch(clip[o], acc, wc, wf, wb);
+        fused[o] = accumulate ? __fadd_rn(fused[o], v) : v;
+      }
+    }
+  }
+}
+
+// CSR flavour (exact rescoring of candidates): one 8-lane group per CSR entry.
+__global__ void __launch_bounds__(256)
+frame_fuse_csr_kernel(const float* __restrict__ q, const float* __restrict__ table,
+                      const float* __restrict__ clip, const int32_t* __restrict__ key_clip,
+                      const int32_t* __restrict__ vid_ptr, const int32_t* __restrict__ q_list,
+                      const int32_t* __restrict__ slot, int Nv, int P, int D, float wc, float wf,
+                      float wb, int accumulate, float* __restrict__ cand_scores) {
+  const int n = blockIdx.x;
+  const int e0 = vid_ptr[n], e1 = vid_ptr[n + 1];
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  for (int base = e0 + blockIdx.y * 32; base < e1; base += gridDim.y * 32) {
+    const int e = base + grp;
+    const bool live = e < e1;
+    float acc = 0.f;
+    if (live) {
+      int k = key_clip[e];
+      k = k < 0 ? 0 : (k >= P ? P - 1 : k);
+      acc = RowLoader<float>::dot(q + (int64_t)q_list[e] * D, table + ((int64_t)n * P + k) * D, D, sub);
+    }
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (live && sub == 0) {
+      const float v = fuse_branch(clip[e], acc, wc, wf, wb);
+      const int sl = slot[e];
+      cand_scores[sl] = accumulate ? __fadd_rn(cand_scores[sl], v) : v;
+    }
+  }
+}
+
+__global__ void fuse_scores_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa,
+                                   float wb, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(wa, a[i]), __fmul_rn(wb, b[i]));
+}
+
+}  // namespace dkd
+
+using namespace dkd;
+
+template <int kRows, int kEpi>
+static int launch_dots(const DotsParams& p, int Nv, int tiles, cudaStream_t st) {
+  if (Nv == 0 || tiles == 0) return DKD_OK;
+  dim3 grid(Nv, tiles);
+  dots_kernel<kRows, kEpi><<<grid, 256, 0, st>>>(p);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, int32_t R,
+                                 int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg,
+                                 int64_t ld_out, float* out_rows, const int32_t* vid_ptr,
+                                 const int32_t* q_list, void* stream) {
+  if (!qn || !xn || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
+  if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
+  if (R <= 0 || R > 128 || D <= 0 || D % kKC != 0) return DKD_ERR_SHAPE;
+  if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  if (M > 65535 * kTM) return DKD_ERR_SHAPE;
+  DotsParams p{};
+  p.q = qn; p.q_video_stride = 0; p.M = M; p.x = xn; p.R = R; p.D = D; p.T = 0; p.mask = mask;
+  p.scale = nullptr; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.out_rows = out_rows;
+  p.Nv = Nv; p.vid_ptr = vid_ptr; p.q_list = q_list;
+  const int tiles = (M + kTM - 1) / kTM;
+  if (R <= 32) return launch_dots<32, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
+  if (R <= 64) return launch_dots<64, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
+  return launch_dots<128, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const float* prop_scale,
+                                  int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
+                                  int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
+                                  void* stream) {
+  if (!qn || !clips || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
+  if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
+  if (T <= 0 || T > 32 || D <= 0 || D % kKC != 0) return DKD_ERR_SHAPE;
+  if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  if (M > 65535 * kTM) return DKD_ERR_SHAPE;
+  DotsParams p{};
+  p.q = qn; p.q_video_stride = 0; p.M = M; p.x = clips; p.R = T; p.D = D; p.T = T; p.mask = nullptr;
+  p.scale = prop_scale; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.out_rows = nullptr;
+  p.Nv = Nv; p.vid_ptr = vid_ptr; p.q_list = q_list;
+  return launch_dots<32, EPI_CLIP>(p, Nv, (M + kTM - 1) / kTM, (cudaStream_t)stream);
+}
+
+extern "C" int dkd_key_clip_dots(const float* key, const float* clips, int32_t Nv, int32_t L, int32_t T,
+                                 int32_t D, float* E, void* stream) {
+  if (!key || !clips || !E || Nv < 0) return DKD_ERR_ARG;
+  if (L <= 0 || T <= 0 || T > 32 || D <= 0 || D % kKC != 0) return DKD_ERR_SHAPE;
+  if (Nv == 0) return DKD_OK;
+  DotsParams p{};
+  p.q = key; p.q_video_stride = (int64_t)L * D; p.M = L; p.x = clips; p.R = T; p.D = D; p.T = T;
+  p.out_rows = E; p.Nv = Nv;
+  return launch_dots<32, EPI_STORE>(p, Nv, (L + kTM - 1) / kTM, (cudaStream_t)stream);
+}
+
+extern "C" int dkd_frame_fuse(const void* q, const void* table, int32_t is_bf16, const float* clip_scores,
+                              const int32_t* key_clip, int32_t M, int32_t Nv, int32_t P, int32_t D,
+                              int64_t ld, float w_clip, float w_frame, float w_branch, int32_t accumulate,
+                              float* out_frame, float* fused, void* stream) {
+  if (!q || !table || !key_clip || M < 0 || Nv < 0 || (!out_frame && !fused)) return DKD_ERR_ARG;
+  if (fused && !clip_scores) return DKD_ERR_ARG;
+  if (D <= 0 || D % 64 != 0 || P <= 0) return DKD_ERR_SHAPE;
+  if (ld < Nv) return DKD_ERR_ARG;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  dim3 grid((M + 31) / 32, (Nv + 7) / 8);
+  if (grid.y > 65535) return DKD_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (is_bf16) {
+    frame_fuse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, clip_scores, key_clip, M, Nv, P, D, ld,
+        w_clip, w_frame, w_branch, accumulate, out_frame, fused);
+  } else {
+    frame_fuse_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)table, clip_scores,
+                                                   key_clip, M, Nv, P, D, ld, w_clip, w_frame, w_branch,
+                                                   accumulate, out_frame, fused);
+  }
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_frame_fuse_csr(const float* q, const float* table, const float* clip_scores,
+                                  const int32_t* key_clip, const int32_t* vid_ptr, const int32_t* q_list,
+                                  const int32_t* slot, int32_t Nv, int32_t P, int32_t D, float w_clip,
+                                  float w_frame, float w_branch, int32_t accumulate, float* cand_scores,
+                                  void* stream) {
+  if (!q || !table || !clip_scores || !key_clip || !vid_ptr || !q_list || !slot || !cand_scores || Nv < 0)
+    return DKD_ERR_ARG;
+  if (D <= 0 || D % 32 != 0 || P <= 0) return DKD_ERR_SHAPE;
+  if (Nv == 0) return DKD_OK;
+  dim3 grid(Nv, 4);
+  frame_fuse_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, table, clip_scores, key_clip, vid_ptr,
+                                                                q_list, slot, Nv, P, D, w_clip, w_frame,
+                                                                w_branch, accumulate, cand_scores);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_fuse_scores(const float* a, const float* b, float wa, float wb, float* out, int64_t n,
+                               void* stream) {
+  if (!a || !b || !out || n < 0) return DKD_ERR_ARG;
+  if (n == 0) return DKD_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fuse_scores_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, wa, wb, out, n);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}

@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (include/dkd_b200.h).
+
+PyTorch is plumbing here: it allocates device buffers and provides the current stream; every
+number is produced by the hand-written kernels in csrc/.  All inputs must be CUDA tensors.
+"""
+import torch
+
+from . import _lib
+
+T_CLIPS = 32  # clips per video of the two-scale head (map_size); P = T(T+1)/2 = 528
+
+
+def num_proposals(T: int = T_CLIPS) -> int:
+    return T * (T + 1) // 2
+
+
+def proposal_index(w: int, s: int, T: int = T_CLIPS) -> int:
+    """Index of the window (length w, start s): SURVEY §8 N2 ordering."""
+    return (w - 1) * T - ((w - 1) * (w - 2)) // 2 + s
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DkdError(f"{name}: expected a CUDA tensor (dkd_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.DkdError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.DkdError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def normalize_rows(x, want_f32=True, want_bf16=False, rows_pad=None, eps=1e-12):
+    """F.normalize(x, dim=-1) (method/model.py:318-319) -> (fp32 | None, bf16 | None), each (rows_pad, D)."""
+    _chk(x, torch.float32, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    rows_pad = rows if rows_pad is None else rows_pad
+    of = torch.empty((rows_pad, D), dtype=torch.float32, device=x.device) if want_f32 else None
+    ob = torch.empty((rows_pad, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _lib.call("dkd_normalize_rows", _p(x), rows, D, eps, _p(of), _p(ob), rows_pad, _stream())
+    return of, ob
+
+
+def downsample_clips(frames, lengths, T=T_CLIPS):
+    """average_to_fixed_length (method/data_provider.py:30-50) per video: (Nv, L, D) -> (Nv, T, D)."""
+    _chk(frames, torch.float32, "frames")
+    _chk(lengths, torch.int32, "lengths")
+    Nv, L, D = frames.shape
+    clips = torch.empty((Nv, T, D), dtype=torch.float32, device=frames.device)
+    _lib.call("dkd_downsample_clips", _p(frames), _p(lengths), Nv, L, D, T, _p(clips), _stream())
+    return clips
+
+
+def build_proposals(clips, want_bf16=True, want_scale=True, want_f32=False):
+    """(Nv, T, D) clips -> (prop_bf16 (Nv,P,D) normalised, prop_scale (Nv,P), prop_f32 (Nv,P,D) means)."""
+    _chk(clips, torch.float32, "clips")
+    Nv, T, D = clips.shape
+    P = num_proposals(T)
+    dev = clips.device
+    pb = torch.empty((Nv, P, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    ps = torch.empty((Nv, P), dtype=torch.float32, device=dev) if want_scale else None
+    pf = torch.empty((Nv, P, D), dtype=torch.float32, device=dev) if want_f32 else None
+    _lib.call("dkd_build_proposals", _p(clips), Nv, T, D, _p(pb), _p(ps), _p(pf), _stream())
+    return pb, ps, pf
+
+
+def score_max_f32(qn, xn, mask=None, want_rows=False, csr=None):
+    """Exact fp32 get_sim_scores core: qn (M,D), xn (Nv,R,D) normalised -> (max (M,Nv), argmax, rows|None)."""
+    _chk(qn, torch.float32, "qn")
+    _chk(xn, torch.float32, "xn")
+    M, D = qn.shape
+    Nv, R, _ = xn.shape
+    dev = qn.device
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    rows = torch.empty((M, R, Nv), dtype=torch.float32, device=dev) if want_rows else None
+    if csr is None:
+        om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
+        oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
+        _lib.call("dkd_score_max_f32", _p(qn), M, _p(xn), Nv, R, D, _p(mask), _p(om), _p(oa), Nv, _p(rows),
+                  None, None, _stream())
+    else:
+        vid_ptr, q_list = csr
+        E = q_list.numel()
+        om = torch.empty((E,), dtype=torch.float32, device=dev)
+        oa = torch.empty((E,), dtype=torch.int32, device=dev)
+        _lib.call("dkd_score_max_f32", _p(qn), M, _p(xn), Nv, R, D, _p(mask), _p(om), _p(oa), 0, _p(rows),
+                  _p(vid_ptr), _p(q_list), _stream())
+    return om, oa, rows
+
+
+def clip_score_f32(qn, clips, prop_scale, csr=None):
+    """Exact fp32 clip-scale max/argmax over the P proposals via per-clip dots."""
+    _chk(qn, torch.float32, "qn")
+    _chk(clips, torch.float32, "clips")
+    _chk(prop_scale, torch.float32, "prop_scale")
+    M, D = qn.shape
+    Nv, T, _ = clips.shape
+    dev = qn.device
+    if csr is None:
+        om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
+        oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
+        _lib.call("dkd_clip_score_f32", _p(qn), M, _p(clips), _p(prop_scale), Nv, T, D, _p(om), _p(oa), Nv,
+                  None, None, _stream())
+    else:
+        vid_ptr, q_list = csr
+        E = q_list.numel()
+        om = torch.empty((E,), dtype=torch.float32, device=dev)
+        oa = torch.empty((E,), dtype=torch.int32, device=dev)
+        _lib.call("dkd_clip_score_f32", _p(qn), M, _p(clips), _p(prop_scale), Nv, T, D, _p(om), _p(oa), 0,
+                  _p(vid_ptr), _p(q_list), _stream())
+    return om, oa
+
+
+def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None):
+    """tcgen05 GEMM + fused max/argmax: q_bf16 (Mpad,D), x_bf16 (Nv*R, D) -> (max (M,Nv), argmax (M,Nv))."""
+    _chk(q_bf16, torch.bfloat16, "q_bf16")
+    _chk(x_bf16, torch.bfloat16, "x_bf16")
+    Mpad, D = q_bf16.shape
+    if x_bf16.numel() != Nv * R * D:
+        raise _lib.DkdError("x_bf16 does not hold Nv*R rows of D features")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    dev = q_bf16.device
+    om = out_max if out_max is not None else torch.empty((M, Nv), dtype=torch.float32, device=dev)
+    oa = out_arg if out_arg is not None else torch.empty((M, Nv), dtype=torch.int32, device=dev)
+    _lib.call("dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D, _p(mask), _p(om), _p(oa), Nv,
+              _stream())
+    return om, oa
+
+
+def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):
+    """Key-clip-guided attention outputs for every proposal of every video -> (Nv,P,D)."""
+    _chk(key, torch.float32, "key")
+    _chk(val, torch.float32, "val")
+    _chk(clips, torch.float32, "clips")
+    _chk(lengths, torch.int32, "lengths")
+    Nv, L, D = key.shape
+    T = clips.shape[1]
+    P = num_proposals(T)
+    dev = key.device
+    E = torch.empty((Nv, L, T), dtype=torch.float32, device=dev)
+    _lib.call("dkd_key_clip_dots", _p(key), _p(clips), Nv, L, T, D, _p(E), _stream())
+    tf = torch.empty((Nv, P, D), dtype=torch.float32, device=dev) if want_f32 else None
+    tb = torch.empty((Nv, P, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    _lib.call("dkd_frame_attn_table", _p(E), _p(val), _p(lengths), Nv, L, T, D, _p(tf), _p(tb), _stream())
+    return tf, tb
+
+
+def frame_fuse(q, table, clip_scores, key_clip, w_clip, w_frame, w_branch, fused=None, accumulate=False,
+               want_frame=False):
+    """frame[m,n] = q[m].table[n,key_clip[m,n]]; fused (+)= w_branch*(w_clip*clip + w_frame*frame)."""
+    is_bf16 = q.dtype == torch.bfloat16
+    _chk(q, torch.bfloat16 if is_bf16 else torch.float32, "q")
+    _chk(table, q.dtype, "table")
+    _chk(key_clip, torch.int32, "key_clip")
+    _chk(clip_scores, torch.float32, "clip_scores")
+    M, Nv = key_clip.shape
+    _, P, D = table.shape
+    dev = key_clip.device
+    fr = torch.empty((M, Nv), dtype=torch.float32, device=dev) if want_frame else None
+    if fused is None:
+        fused = torch.empty((M, Nv), dtype=torch.float32, device=dev)
+        accumulate = False
+    _lib.call("dkd_frame_fuse", _p(q), _p(table), int(is_bf16), _p(clip_scores), _p(key_clip), M, Nv, P, D, Nv,
+              w_clip, w_frame, w_branch, int(accumulate), _p(fr), _p(fused), _stream())
+    return fused, fr
+
+
+def fuse_scores(a, b, wa=0.7, wb=0.3):
+    """fl(wa*a) + fl(wb*b): the numpy fusion of method/eval.py:254, bit-exact."""
+    _chk(a, torch.float32, "a")
+    _chk(b, torch.float32, "b")
+    out = torch.empty_like(a)
+    _lib.call("dkd_fuse_scores", _p(a), _p(b), wa, wb, _p(out), a.numel(), _stream())
+    return out
+
+
+def topk(scores, K, id_base=0):
+    """Per-row top-K (score desc, id asc) of a dense (M, Nv) matrix -> (scores (M,K), ids (M,K) int32)."""
+    _chk(scores, torch.float32, "scores")
+    M, Nv = scores.shape
+    os_ = torch.empty((M, K), dtype=torch.float32, device=scores.device)
+    oi = torch.empty((M, K), dtype=torch.int32, device=scores.device)
+    _lib.call("dkd_topk", _p(scores), M, Nv, Nv, K, id_base, _p(os_), _p(oi), _stream())
+    return os_, oi
+
+
+def merge_topk(scores, ids):
+    """(G, M, K) shard lists -> merged (M, K)."""
+    _chk(scores, torch.float32, "scores")
+    _chk(ids, torch.int32, "ids")
+    G, M, K = scores.shape
+    os_ = torch.empty((M, K), dtype=torch.float32, device=scores.device)
+    oi = torch.empty((M, K), dtype=torch.int32, device=scores.device)
+    _lib.call("dkd_merge_topk", _p(scores), _p(ids), G, M, K, _p(os_), _p(oi), _stream())
+    return os_, oi
+
+
+def rank_of_gt(scores, gt_ptr, gt_ids):
+    """1-based rank of the best-ranked GT video per query (eval_q2m, method/eval.py:73-82)."""
+    _chk(scores, torch.float32, "scores")
+    _chk(gt_ptr, torch.int32, "gt_ptr")
+    _chk(gt_ids, torch.int32, "gt_ids")
+    M, Nv = scores.shape
+    out = torch.empty((M,), dtype=torch.int32, device=scores.device)
+    _lib.call("dkd_rank_of_gt", _p(scores), M, Nv, Nv, _p(gt_ptr), _p(gt_ids), _p(out), _stream())
+    return out
+
+
+def candidates_to_csr(cand_ids, Nv, id_base=0):
+    """(M, K) candidate video ids -> per-video CSR (vid_ptr (Nv+1), q_list (M*K), slot (M*K))."""
+    _chk(cand_ids, torch.int32, "cand_ids")
+    M, K = cand_ids.shape
+    dev = cand_ids.device
+    counts = torch.empty((Nv,), dtype=torch.int32, device=dev)
+    vid_ptr = torch.empty((Nv + 1,), dtype=torch.int32, device=dev)
+    q_list = torch.zeros((M * K,), dtype=torch.int32, device=dev)
+    slot = torch.zeros((M * K,), dtype=torch.int32, device=dev)
+    _lib.call("dkd_candidates_to_csr", _p(cand_ids), M, K, Nv, id_base, _p(counts), _p(vid_ptr), _p(q_list),
+              _p(slot), _stream())
+    return vid_ptr, q_list, slot
+
+
+def frame_fuse_csr(q, table, clip_scores, key_clip, csr, w_clip, w_frame, w_branch, cand_scores, accumulate):
+    _chk(q, torch.float32, "q")
+    _chk(table, torch.float32, "table")
+    vid_ptr, q_list, slot = csr
+    Nv, P, D = table.shape
+    _lib.call("dkd_frame_fuse_csr", _p(q), _p(table), _p(clip_scores), _p(key_clip), _p(vid_ptr), _p(q_list),
+              _p(slot), Nv, P, D, w_clip, w_frame, w_branch, int(accumulate), _p(cand_scores), _stream())
+    return cand_scores
+
+
+def sort_candidates(cand_scores, cand_ids, K_out):
+    _chk(cand_scores, torch.float32, "cand_scores")
+    _chk(cand_ids, torch.int32, "cand_ids")
+    M, K = cand_ids.shape
+    os_ = torch.empty((M, K_out), dtype=torch.float32, device=cand_ids.device)
+    oi = torch.empty((M, K_out), dtype=torch.int32, device=cand_ids.device)
+    _lib.call("dkd_sort_candidates", _p(cand_scores), _p(cand_ids), M, K, K_out, _p(os_), _p(oi), _stream())
+    return os_, oi

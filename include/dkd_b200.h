@@ -1,0 +1,183 @@
+/*
+ * dkd_b200.h — C ABI of the B200-native DL-DKD++ corpus retrieval scoring path.
+ *
+ * The reference (HuiGuanLab/DL-DKD) has no FFI: its seam for this path is plain Python
+ * (bound methods of DLDKD(nn.Module), method/model.py, and module functions of
+ * method/eval.py).  Each entry point below names the reference interface (file:line under
+ * /root/reference) whose arithmetic it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - no allocation, no host synchronisation, no global state inside any call
+ *     (exception: dkd_score_rank_host, the host-buffer convenience entry, which
+ *     synchronises `stream` before returning);
+ *   - return value: 0 = ok, <0 = DKD_ERR_* (bad argument), >0 = cudaError_t;
+ *   - dense score matrices are query-major: element (m, n) at out[m * ld + n];
+ *   - "rows per video" R: the scoring kernels see the corpus as Nv * R rows of D
+ *     features; R = L (frames, reference path) or R = P = T(T+1)/2 (clip proposals).
+ *
+ * All arithmetic types: fp32 scores, int32 indices, bf16 (uint16_t storage) GEMM operands.
+ */
+#ifndef DKD_B200_H_
+#define DKD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKD_OK 0
+#define DKD_ERR_ARG (-1)       /* null pointer / non-positive size */
+#define DKD_ERR_SHAPE (-2)     /* unsupported shape (D % 64, T > 32, K > 256, ...) */
+#define DKD_ERR_ALIGN (-3)     /* pointer or leading dimension not aligned as required */
+#define DKD_ERR_DRIVER (-4)    /* cuTensorMapEncodeTiled unavailable */
+#define DKD_ERR_WORKSPACE (-5) /* workspace too small */
+
+#define DKD_MASKED_SCORE (-1e10f) /* method/model.py:444-445 mask_logits fill value */
+
+int dkd_version(void);
+const char* dkd_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * Row preparation: L2-normalise every D-vector (x / max(||x||, eps)), write fp32 and/or bf16.
+ * Replaces F.normalize(modularied_query) / F.normalize(context_feat), method/model.py:318-319
+ * (hoisted out of the per-query-batch loop of method/eval.py:188-208).
+ * rows_out_pad >= rows: extra output rows are zero-filled (GEMM M padding). Either output may
+ * be NULL.
+ */
+int dkd_normalize_rows(const float* x, int64_t rows, int32_t D, float eps,
+                       float* out_f32, uint16_t* out_bf16, int64_t rows_out_pad, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Clip downsample: encoded frames (Nv, L, D) + valid lengths -> (Nv, T, D) clip features with
+ * the arithmetic of average_to_fixed_length, method/data_provider.py:30-50.
+ */
+int dkd_downsample_clips(const float* frames, const int32_t* lengths, int32_t Nv, int32_t L,
+                         int32_t D, int32_t T, float* clips, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Clip-proposal builder (north_star "prefix-sum kernel"): for every video the
+ * P = T(T+1)/2 sliding-window means, ordered by window length w = 1..T then start s,
+ *   p(w, s) = (w-1)*T - (w-1)(w-2)/2 + s,   prop[p] = mean(clips[s : s+w]).
+ * Outputs (any may be NULL):
+ *   prop_bf16   (Nv, P, D)  L2-normalised proposals, bf16 — B operand of the clip-scale GEMM;
+ *   prop_scale  (Nv, P)     1 / (w * max(||mean||, 1e-12)) — turns a window SUM of per-clip dot
+ *                           products into the cosine (exact fp32 path);
+ *   prop_f32    (Nv, P, D)  un-normalised fp32 means (tests / small shapes only).
+ * Requires T <= 32, D % 64 == 0, D <= 512.
+ */
+int dkd_build_proposals(const float* clips, int32_t Nv, int32_t T, int32_t D,
+                        uint16_t* prop_bf16, float* prop_scale, float* prop_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Exact fp32 scoring (SIMT).  Replaces DLDKD.get_sim_scores, method/model.py:307-329, with the
+ * corpus normalisation hoisted:
+ *   out_max[m, n] = max_r  qn[m] . xn[n, r]   (masked rows score exactly -1e10, mask_logits :444)
+ *   out_arg[m, n] = first r attaining the max (torch.max tie rule)
+ * qn (M, D) and xn (Nv, R, D) are L2-normalised fp32; mask (Nv, R) uint8 or NULL; R <= 128.
+ * out_rows (optional) is the reference's second return value laid out (M, R, Nv).
+ * q_list / vid_ptr (optional, both or neither): CSR restriction — for video n only queries
+ * q_list[vid_ptr[n] .. vid_ptr[n+1]) are scored and results go to out_max[e] / out_arg[e]
+ * (entry order) instead of the dense matrix.
+ */
+int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, int32_t R,
+                      int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg,
+                      int64_t ld_out, float* out_rows, const int32_t* vid_ptr,
+                      const int32_t* q_list, void* stream);
+
+/* Exact fp32 clip-scale scores through per-clip dot products (SURVEY §7 "linearity"):
+ *   d[m, n, i] = qn[m] . clips[n, i];  S[m, n, p(w,s)] = (sum_{i=s}^{s+w-1} d[m,n,i]) * prop_scale[n, p]
+ *   out_max = max_p S, out_arg = first argmax_p.  Same CSR option as above. T <= 32.
+ * Replaces get_clip_scale_scores of the two-scale head, fp32 reference flavour.
+ */
+int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const float* prop_scale,
+                       int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
+                       int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * bf16 tcgen05/TMEM scoring GEMM with fused max/argmax epilogue (the hot kernel).
+ *   q_bf16 (Mpad, D) normalised queries, Mpad % 128 == 0, rows >= M zero;
+ *   x_bf16 (Nv * R, D) normalised corpus rows; R % 16 == 0, D % 64 == 0, D <= 512;
+ *   mask   (Nv, R) uint8 or NULL.
+ * Outputs as dkd_score_max_f32 (dense only).  Replaces method/model.py:318-327 (R = L) and the
+ * clip-scale contraction of SURVEY §8 N3 (R = P = 528).
+ * TMA descriptors are encoded on the host per call (cuTensorMapEncodeTiled fetched through
+ * cudaGetDriverEntryPoint) and passed as kernel parameters: no workspace.
+ */
+int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
+                       int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                       int32_t* out_arg, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Key-clip-guided frame attention, query-independent table form:
+ *   E[n, l, i]      = key[n, l] . clips[n, i]                       (dkd_key_clip_dots)
+ *   logit[n, p, l]  = (sum_{i in window p} E[n, l, i]) / w
+ *   a               = softmax over valid frames l < lengths[n]
+ *   g[n, p]         = sum_l a_l * val[n, l];   table = g / max(||g||, 1e-12)
+ * key/val (Nv, L, D) fp32 are the W_k / W_v projections of the encoded frames.
+ * Outputs (either may be NULL): table_f32, table_bf16 (Nv, P, D). L <= 128, T <= 32, D % 64 == 0,
+ * D <= 512.  E is a caller-provided scratch of Nv*L*T floats.
+ */
+int dkd_key_clip_dots(const float* key, const float* clips, int32_t Nv, int32_t L, int32_t T,
+                      int32_t D, float* E, void* stream);
+int dkd_frame_attn_table(const float* E, const float* val, const int32_t* lengths, int32_t Nv,
+                         int32_t L, int32_t T, int32_t D, float* table_f32, uint16_t* table_bf16,
+                         void* stream);
+
+/* Frame-scale score + branch fusion (cross-branch weights method/eval.py:254):
+ *   frame[m, n]  = q[m] . table[n, key_clip[m, n]]
+ *   branch[m, n] = fl(w_clip * clip[m, n]) + fl(w_frame * frame[m, n])
+ *   fused[m, n]  = accumulate ? fused[m, n] + fl(w_branch * branch) : fl(w_branch * branch)
+ * q/table both fp32 (is_bf16 = 0) or both bf16 (is_bf16 = 1).  out_frame / fused may be NULL.
+ */
+int dkd_frame_fuse(const void* q, const void* table, int32_t is_bf16, const float* clip_scores,
+                   const int32_t* key_clip, int32_t M, int32_t Nv, int32_t P, int32_t D,
+                   int64_t ld, float w_clip, float w_frame, float w_branch, int32_t accumulate,
+                   float* out_frame, float* fused, void* stream);
+
+/* fused = fl(wa * a) + fl(wb * b), elementwise, numpy rounding order of method/eval.py:254. */
+int dkd_fuse_scores(const float* a, const float* b, float wa, float wb, float* out, int64_t n,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Ranking.  dkd_topk: per query the K best (score desc, video id asc on equal scores) of a
+ * dense (M, Nv) matrix; ids are offset by id_base (global ids of a corpus shard). K <= 256.
+ * Replaces the np.argsort of eval_q2m, method/eval.py:75 (only the top-100 matter for R@K).
+ */
+int dkd_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, int32_t K, int32_t id_base,
+             float* out_scores, int32_t* out_ids, void* stream);
+
+/* Merge G per-shard top-K lists (G, M, K) (e.g. after an NCCL all-gather) into one (M, K). */
+int dkd_merge_topk(const float* scores, const int32_t* ids, int32_t G, int32_t M, int32_t K,
+                   float* out_scores, int32_t* out_ids, void* stream);
+
+/* Rank of the best ground-truth video per query (1-based), eval_q2m method/eval.py:73-82:
+ * rank = 1 + #{n : s[n] > s[gt]} + #{n < gt : s[n] == s[gt]}, min over the query's GT list
+ * (CSR gt_ptr / gt_ids).  Dense scores. */
+int dkd_rank_of_gt(const float* scores, int32_t M, int32_t Nv, int64_t ld, const int32_t* gt_ptr,
+                   const int32_t* gt_ids, int32_t* out_rank, void* stream);
+
+/* Candidate bookkeeping for exact rescoring: invert (M, K) candidate ids into a per-video CSR.
+ * Candidate ids are global (id_base + local video index); ids outside the shard are skipped.
+ * counts (Nv) scratch; vid_ptr (Nv+1), q_list (M*K), slot (M*K) outputs. */
+int dkd_candidates_to_csr(const int32_t* cand_ids, int32_t M, int32_t K, int32_t Nv,
+                          int32_t id_base, int32_t* counts, int32_t* vid_ptr, int32_t* q_list,
+                          int32_t* slot, void* stream);
+/* Per-CSR-entry frame score + fusion (exact rescoring of candidates), then scatter to (M, K). */
+int dkd_frame_fuse_csr(const float* q, const float* table, const float* clip_scores,
+                       const int32_t* key_clip, const int32_t* vid_ptr, const int32_t* q_list,
+                       const int32_t* slot, int32_t Nv, int32_t P, int32_t D, float w_clip,
+                       float w_frame, float w_branch, int32_t accumulate, float* cand_scores,
+                       void* stream);
+/* Sort each query's K candidates (score desc, id asc) and keep the first K_out. */
+int dkd_sort_candidates(const float* cand_scores, const int32_t* cand_ids, int32_t M, int32_t K,
+                        int32_t K_out, float* out_scores, int32_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKD_B200_H_ */

@@ -1,0 +1,225 @@
+"""CPU oracle for the DL-DKD++ corpus retrieval scoring path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module, and only as the checker or the timed CPU baseline — never as a product path.
+
+Two groups:
+
+(a-REF)  restatements of code that EXISTS in the reference; every function cites the reference
+         file:line it follows.  These are PINNED: tests/golden/ref_*.npz were produced by running
+         the unmodified reference (/root/reference, imported through oracle/ref_shim.py) and
+         tests/test_oracle_golden.py checks this file against them.
+
+(a-NS)   the two-scale head north_star names (clip proposals + key-clip-guided frame attention).
+         It does not exist under /root/reference (SURVEY §8 a-NS) — PARITY UNPINNED by the
+         reference: this restatement of the MS-SL formulation is the normative spec; its only
+         external anchors are the reference primitives it composes (average_to_fixed_length,
+         F.normalize / einsum / torch.max conventions of get_sim_scores, the 0.7/0.3 fusion).
+
+Plain PyTorch fp32 on CPU, written for clarity (direct formulas, no algebraic shortcuts).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MASK_FILL = -1e10  # method/model.py:444-445
+
+
+# ----------------------------------------------------------------------------------- (a-REF)
+def mask_logits(target, mask):
+    """method/model.py:444-445."""
+    return target * mask + (1 - mask) * MASK_FILL
+
+
+def get_sim_scores(query, context, mask=None):
+    """DLDKD.get_sim_scores, method/model.py:307-329.
+
+    query (M, D), context (N, L, D), mask (N, L) float {0,1}.
+    Returns (scores (M, N), per_row (M, L, N), argmax (M, N) int64); the reference computes the
+    argmax at :327 and drops it.
+    """
+    q = F.normalize(query, dim=-1)
+    c = F.normalize(context, dim=-1)
+    per_row = torch.einsum("md,nld->mln", q, c)
+    if mask is not None:
+        per_row = mask_logits(per_row, mask.transpose(0, 1).unsqueeze(0))
+    scores, idx = torch.max(per_row, dim=1)
+    return scores, per_row, idx
+
+
+def get_unnormalized_sim_scores(query, context, mask=None):
+    """DLDKD.get_unnormalized_sim_scores, method/model.py:331-350."""
+    per_row = torch.einsum("md,nld->mln", query, context)
+    if mask is not None:
+        per_row = mask_logits(per_row, mask.transpose(0, 1).unsqueeze(0))
+    return torch.max(per_row, dim=1)[0]
+
+
+def fuse_branches(inher_scores, explore_scores, w_inher=0.7, w_explore=0.3):
+    """eval_epoch fusion, method/eval.py:254 (numpy fp32)."""
+    return w_inher * np.asarray(inher_scores, dtype=np.float32) + w_explore * np.asarray(explore_scores, dtype=np.float32)
+
+
+def get_gt(video_metas, query_metas):
+    """method/eval.py:43-57 (dictionary instead of the O(Nv*Nq) double loop; same output)."""
+    pos = {v: i for i, v in enumerate(video_metas)}
+    v2t = [[] for _ in video_metas]
+    for qi, qid in enumerate(query_metas):
+        vi = pos.get(qid.split('#', 1)[0])
+        if vi is not None:
+            v2t[vi].append(qi)
+    t2v = {}
+    for vi, qs in enumerate(v2t):
+        for qi in qs:
+            t2v.setdefault(qi, []).append(vi)
+    return v2t, t2v
+
+
+def gt_ranks(neg_scores, q2m_gts, stable=True):
+    """Rank (1-based) of the best ground-truth item per query, eval_q2m method/eval.py:69-82.
+
+    The reference sorts with np.argsort (quicksort: order of exactly tied scores unspecified);
+    stable=True fixes the documented tie rule "lower video index first".
+    """
+    n_q, n_m = neg_scores.shape
+    ranks = np.zeros((n_q,), np.int32)
+    for i in range(n_q):
+        order = np.argsort(neg_scores[i], kind="stable" if stable else "quicksort")
+        inv = np.empty(n_m, np.int64)
+        inv[order] = np.arange(n_m)
+        ranks[i] = min((inv[k] + 1 for k in q2m_gts[i]), default=n_m + 1)
+    return ranks
+
+
+def eval_q2m(neg_scores, q2m_gts):
+    """method/eval.py:59-94: (r1, r5, r10, r100, medr, meanr) from NEGATED scores."""
+    r = gt_ranks(neg_scores, q2m_gts)
+    n_q = neg_scores.shape[0]
+    rk = [100.0 * np.count_nonzero(r <= k) / n_q for k in (1, 5, 10, 100)]
+    return (rk[0], rk[1], rk[2], rk[3], float(np.median(r)), float(r.mean()))
+
+
+def t2v_map(neg_scores, t2v_gts):
+    """method/eval.py:97-111 with ap_score :26-41: only the first GT counts => mean(1 / rank)."""
+    first = {i: [g[0]] for i, g in t2v_gts.items()}
+    r = gt_ranks(neg_scores, first)
+    return float(np.mean(1.0 / r))
+
+
+def recall_from_topk(topk_ids, q2m_gts, ks=(1, 5, 10, 100)):
+    """R@K from per-query ranked id lists (what the GPU path returns)."""
+    n_q = topk_ids.shape[0]
+    out = []
+    for k in ks:
+        hit = 0
+        for i in range(n_q):
+            gts = set(q2m_gts[i])
+            hit += any(int(v) in gts for v in topk_ids[i, :k])
+        out.append(100.0 * hit / n_q)
+    return tuple(out)
+
+
+def average_to_fixed_length(x, map_size):
+    """method/data_provider.py:30-50.  x: (n, D) torch tensor -> (map_size, D)."""
+    n = x.shape[0]
+    idxs = torch.arange(0, map_size + 1, 1.0) / map_size * n
+    idxs = torch.min(torch.round(idxs).long(), torch.tensor(n - 1))
+    out = []
+    for i in range(map_size):
+        s, e = idxs[i].item(), idxs[i + 1].item()
+        out.append(torch.mean(x[s:e], dim=0) if s < e else x[s])
+    return torch.stack(out, dim=0)
+
+
+def l2_normalize_np_array(a, eps=1e-5):
+    """method/data_provider.py:71-73."""
+    return a / (np.linalg.norm(a, axis=-1, keepdims=True) + eps)
+
+
+# ------------------------------------------------------------------------------------ (a-NS)
+def num_proposals(T):
+    return T * (T + 1) // 2
+
+
+def proposal_index(w, s, T):
+    return (w - 1) * T - ((w - 1) * (w - 2)) // 2 + s
+
+
+def downsample_clips(frames, lengths, T=32):
+    """N1: average_to_fixed_length on each video's valid encoded frames. (Nv, L, D) -> (Nv, T, D)."""
+    return torch.stack([average_to_fixed_length(frames[n, : int(lengths[n])], T) for n in range(frames.shape[0])])
+
+
+def build_proposals(clips):
+    """N2: (Nv, T, D) -> (Nv, P, D): window length w = 1..T (Identity, then AvgPool1d(w, stride 1)), start s."""
+    Nv, T, D = clips.shape
+    x = clips.transpose(1, 2)  # (Nv, D, T)
+    outs = [clips]
+    for w in range(2, T + 1):
+        outs.append(F.avg_pool1d(x, kernel_size=w, stride=1).transpose(1, 2))
+    return torch.cat(outs, dim=1)
+
+
+def clip_scale_scores(query, proposals):
+    """N3: cosine of every query against every proposal, max / first argmax over proposals.
+
+    query (M, D), proposals (Nv, P, D) -> (s_clip (M, Nv), key_clip (M, Nv) int64, all (M, P, Nv)).
+    Same conventions as get_sim_scores (F.normalize eps, einsum layout, torch.max over dim 1).
+    """
+    return get_sim_scores(query, proposals, None)
+
+
+def key_clip_guided_attention(key, val, mask, proposals, key_clip):
+    """N4 (inference, all pairs): key/val (Nv, L, D) = W_k F, W_v F; mask (Nv, L); proposals
+    (Nv, P, D) un-normalised means; key_clip (M, Nv).  Returns g (M, Nv, D).
+
+    logits[m, n, l] = key[n, l] . proposals[n, key_clip[m, n]]   (no 1/sqrt(d) scaling)
+    a = softmax over frames with masked frames filled with -1e10; g = sum_l a_l val[n, l].
+    """
+    M, Nv = key_clip.shape
+    g = torch.empty(M, Nv, key.shape[-1])
+    for n in range(Nv):
+        pk = proposals[n, key_clip[:, n]]                      # (M, D)
+        logits = pk @ key[n].T                                  # (M, L)
+        logits = mask_logits(logits, mask[n].unsqueeze(0))
+        a = torch.softmax(logits, dim=-1)
+        g[:, n] = a @ val[n]
+    return g
+
+
+def frame_scale_scores(query, g):
+    """N5: cos(q_m, g[m, n])."""
+    return torch.einsum("md,mnd->mn", F.normalize(query, dim=-1), F.normalize(g, dim=-1))
+
+
+def attention_table(key, val, mask, proposals):
+    """Query-independent form of N4: attention output for EVERY proposal of every video, (Nv, P, D).
+    key_clip_guided_attention(...)[m, n] == attention_table(...)[n, key_clip[m, n]]."""
+    Nv, P, D = proposals.shape
+    out = torch.empty(Nv, P, D)
+    for n in range(Nv):
+        logits = proposals[n] @ key[n].T
+        logits = mask_logits(logits, mask[n].unsqueeze(0))
+        out[n] = torch.softmax(logits, dim=-1) @ val[n]
+    return out
+
+
+def two_scale_branch(query, frames, mask, key_w, key_b, val_w, val_b, T=32, w_clip=0.7, w_frame=0.3):
+    """N6 for one branch: encoded query vectors (M, D) and encoded frames (Nv, L, D) ->
+    dict(clip, key_clip, frame, branch) with branch = w_clip*clip + w_frame*frame."""
+    lengths = mask.sum(dim=1).long()
+    clips = downsample_clips(frames, lengths, T)
+    props = build_proposals(clips)
+    s_clip, _, key_clip = clip_scale_scores(query, props)
+    key = F.linear(frames, key_w, key_b)
+    val = F.linear(frames, val_w, val_b)
+    g = key_clip_guided_attention(key, val, mask, props, key_clip)
+    s_frame = frame_scale_scores(query, g)
+    return dict(clip=s_clip, key_clip=key_clip, frame=s_frame, branch=w_clip * s_clip + w_frame * s_frame,
+                clips=clips, proposals=props)
+
+
+def topk_ids(scores, K):
+    """Ranked ids per query: score descending, lower id first on exact ties."""
+    order = np.argsort(-np.asarray(scores), axis=1, kind="stable")
+    return order[:, :K]

@@ -1,0 +1,297 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): fp32 paths 2e-6 abs on cosine scores (summation order only); bf16 GEMM path
+1e-3 abs vs fp32, and 2e-5 vs an fp32 evaluation of the SAME bf16-rounded operands; indices exact
+except where the oracle's own top-2 gap is below the stated noise floor.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-6
+BF16_TOL = 1e-3
+
+
+def _cuda(*ts):
+    return [t.cuda().contiguous() for t in ts]
+
+
+def _argmax_ok(got, ref_scores_all, ref_arg, tol):
+    """got/ref_arg (M, N); ref_scores_all (M, R, N). Mismatches allowed only if the oracle's score at the
+    kernel's index is within tol of the oracle max (a near tie)."""
+    got = got.long()
+    bad = got != ref_arg
+    if not bad.any():
+        return True, 0
+    m, n = torch.nonzero(bad, as_tuple=True)
+    s_got = ref_scores_all[m, got[m, n], n]
+    s_ref = ref_scores_all[m, ref_arg[m, n], n]
+    return bool(((s_ref - s_got).abs() <= tol).all()), int(bad.sum())
+
+
+def test_normalize_rows(ops):
+    x = torch.randn(300, 384, generator=torch.Generator().manual_seed(1))
+    x[7] = 0.0  # zero row: F.normalize gives zeros (eps clamp)
+    (xc,) = _cuda(x)
+    f32, b16 = ops.normalize_rows(xc, want_f32=True, want_bf16=True, rows_pad=384)
+    ref = F.normalize(x, dim=-1)
+    assert torch.allclose(f32[:300].cpu(), ref, atol=1e-7, rtol=1e-6)
+    assert torch.equal(f32[300:].cpu(), torch.zeros(84, 384))
+    assert torch.equal(b16[:300].cpu(), f32[:300].cpu().to(torch.bfloat16))
+    assert torch.equal(b16[300:].float().cpu(), torch.zeros(84, 384))
+
+
+@pytest.mark.parametrize("T", [32, 8])
+def test_downsample_clips(ops, T):
+    frames, mask, lengths = synth.encoded_corpus(37, 128, 64, seed=2, min_len=1)
+    fc, lc = _cuda(frames, lengths)
+    got = ops.downsample_clips(fc, lc, T=T).cpu()
+    ref = O.downsample_clips(frames, lengths, T)
+    assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
+
+
+def test_build_proposals(ops):
+    frames, mask, lengths = synth.encoded_corpus(19, 128, 384, seed=3)
+    clips = O.downsample_clips(frames, lengths, 32)
+    (cc,) = _cuda(clips)
+    pb, ps, pf = ops.build_proposals(cc, want_bf16=True, want_scale=True, want_f32=True)
+    ref = O.build_proposals(clips)  # (Nv, 528, D)
+    assert pf.shape == ref.shape == (19, 528, 384)
+    assert torch.allclose(pf.cpu(), ref, atol=1e-6, rtol=1e-5)
+    refn = F.normalize(ref, dim=-1)
+    assert (pb.float().cpu() - refn).abs().max() <= 2 ** -8 * refn.abs().max() + 1e-6
+    # prop_scale = 1 / (w * ||mean||)
+    w = torch.cat([torch.full((32 - k + 1,), float(k)) for k in range(1, 33)])
+    ref_scale = 1.0 / (w[None, :] * ref.norm(dim=-1))
+    assert torch.allclose(ps.cpu(), ref_scale, rtol=2e-6)
+    # index formula
+    assert O.proposal_index(1, 0, 32) == 0 and O.proposal_index(32, 0, 32) == 527
+    assert ops.proposal_index(2, 5, 32) == 32 + 5
+
+
+@pytest.mark.parametrize("M,Nv,L,D", [(50, 23, 128, 384), (130, 9, 77, 64), (1, 3, 16, 512), (64, 5, 128, 32)])
+def test_score_max_f32_matches_get_sim_scores(ops, M, Nv, L, D):
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=10 + M)
+    q = synth.encoded_queries(M, D, seed=20 + M)
+    s_ref, rows_ref, a_ref = O.get_sim_scores(q, frames, mask)
+    qc, fc, mc = _cuda(q, frames, mask.to(torch.uint8))
+    qn, _ = ops.normalize_rows(qc)
+    xn, _ = ops.normalize_rows(fc)
+    om, oa, rows = ops.score_max_f32(qn, xn.view(Nv, L, D), mc, want_rows=True)
+    assert (om.cpu() - s_ref).abs().max() <= FP32_TOL
+    rows = rows.cpu()
+    valid = (mask.T[None] > 0).expand_as(rows_ref)
+    assert (rows[valid] - rows_ref[valid]).abs().max() <= FP32_TOL
+    assert torch.equal(rows[~valid], torch.full_like(rows[~valid], -1e10))  # mask_logits fill, exact
+    ok, nbad = _argmax_ok(oa.cpu(), rows_ref, a_ref, FP32_TOL)
+    assert ok, f"{nbad} argmax mismatches beyond fp32 ties"
+
+
+def test_score_max_f32_no_mask_and_fully_masked_video(ops):
+    frames, mask, lengths = synth.encoded_corpus(6, 32, 64, seed=5)
+    q = synth.encoded_queries(10, 64, seed=6)
+    mask2 = mask.clone()
+    mask2[2] = 0  # never happens in the reference data (len >= 1) but must not crash: all -1e10, idx 0
+    s_ref, _, a_ref = O.get_sim_scores(q, frames, mask2)
+    qc, fc, mc = _cuda(q, frames, mask2.to(torch.uint8))
+    qn, _ = ops.normalize_rows(qc)
+    xn, _ = ops.normalize_rows(fc)
+    om, oa, _ = ops.score_max_f32(qn, xn.view(6, 32, 64), mc)
+    assert (om.cpu() - s_ref).abs().max() <= FP32_TOL
+    assert torch.equal(om[:, 2].cpu(), torch.full((10,), -1e10))
+    assert torch.equal(oa[:, 2].cpu().long(), a_ref[:, 2])
+    s_ref2, _, _ = O.get_sim_scores(q, frames, None)
+    om2, _, _ = ops.score_max_f32(qn, xn.view(6, 32, 64), None)
+    assert (om2.cpu() - s_ref2).abs().max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("M,Nv,D", [(70, 11, 384), (5, 3, 64)])
+def test_clip_score_f32(ops, M, Nv, D):
+    frames, mask, lengths = synth.encoded_corpus(Nv, 128, D, seed=31)
+    q = synth.encoded_queries(M, D, seed=32)
+    clips = O.downsample_clips(frames, lengths, 32)
+    props = O.build_proposals(clips)
+    s_ref, all_ref, k_ref = O.clip_scale_scores(q, props)
+    qc, cc = _cuda(q, clips)
+    qn, _ = ops.normalize_rows(qc)
+    _, ps, _ = ops.build_proposals(cc, want_bf16=False)
+    om, oa = ops.clip_score_f32(qn, cc, ps)
+    assert (om.cpu() - s_ref).abs().max() <= FP32_TOL
+    ok, nbad = _argmax_ok(oa.cpu(), all_ref, k_ref, FP32_TOL)
+    assert ok, f"{nbad} key-clip mismatches beyond fp32 ties"
+
+
+@pytest.mark.parametrize("M,Nv,R,D,masked", [
+    (200, 37, 528, 384, False),   # clip-proposal shape, two query tiles, ragged M
+    (50, 23, 128, 384, True),     # reference frame path with mask
+    (128, 300, 528, 384, False),  # many work items
+    (10, 4, 64, 128, True),
+])
+def test_score_max_bf16(ops, M, Nv, R, D, masked):
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(Nv, R, D, generator=g) + 0.5 * torch.randn(Nv, 1, D, generator=g)
+    q = torch.randn(M, D, generator=g)
+    mask = None
+    if masked:
+        lengths = torch.randint(1, R + 1, (Nv,), generator=g)
+        mask = (torch.arange(R)[None] < lengths[:, None]).float()
+    s_ref, rows_ref, a_ref = O.get_sim_scores(q, x, mask)
+    qc, xc = _cuda(q, x)
+    Mpad = ops.round_up(M, 128)
+    _, qb = ops.normalize_rows(qc, want_f32=False, want_bf16=True, rows_pad=Mpad)
+    _, xb = ops.normalize_rows(xc, want_f32=False, want_bf16=True)
+    mc = None if mask is None else mask.to(torch.uint8).cuda()
+    om, oa = ops.score_max_bf16(qb, M, xb, Nv, R, mc)
+    torch.cuda.synchronize()
+    # (1) vs fp32 oracle: north_star tolerance
+    assert (om.cpu() - s_ref).abs().max() <= BF16_TOL
+    # (2) vs fp32 evaluation of the same bf16 operands: accumulate-order noise only
+    qf, xf = qb[:M].float().cpu(), xb.float().cpu().view(Nv, R, D)
+    rows_b = torch.einsum("md,nrd->mrn", qf, xf)
+    if mask is not None:
+        rows_b = O.mask_logits(rows_b, mask.T[None])
+    s_b, a_b = rows_b.max(dim=1)
+    assert (om.cpu() - s_b).abs().max() <= 2e-5
+    ok, nbad = _argmax_ok(oa.cpu(), rows_b, a_b, 2e-5)
+    assert ok, f"{nbad} argmax mismatches vs bf16-operand reference"
+    # (3) vs oracle argmax: only near ties at bf16 resolution may differ
+    ok, nbad = _argmax_ok(oa.cpu(), rows_ref, a_ref, 2 * BF16_TOL)
+    assert ok
+
+
+def _branch_params(D, seed):
+    g = torch.Generator().manual_seed(seed)
+    kw = 0.05 * torch.randn(D, D, generator=g)
+    vw = 0.05 * torch.randn(D, D, generator=g)
+    kb = 0.01 * torch.randn(D, generator=g)
+    vb = 0.01 * torch.randn(D, generator=g)
+    return kw, kb, vw, vb
+
+
+@pytest.mark.parametrize("Nv,L,D", [(7, 128, 384), (5, 50, 64)])
+def test_frame_attn_table(ops, Nv, L, D):
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=41)
+    kw, kb, vw, vb = _branch_params(D, 42)
+    clips = O.downsample_clips(frames, lengths, 32)
+    props = O.build_proposals(clips)
+    key, val = F.linear(frames, kw, kb), F.linear(frames, vw, vb)
+    ref = F.normalize(O.attention_table(key, val, mask, props), dim=-1)
+    kc, vc, cc, lc = _cuda(key, val, clips, lengths)
+    tf, tb = ops.frame_attn_table(kc, vc, cc, lc)
+    assert (tf.cpu() - ref).abs().max() <= 5e-6
+    assert (tb.float().cpu() - ref).abs().max() <= 2 ** -8
+
+
+def test_two_scale_branch_exact_path(ops):
+    """N6 end to end (one branch), exact fp32 kernels vs the oracle."""
+    Nv, L, D, M = 13, 128, 384, 45
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=51)
+    q = synth.encoded_queries(M, D, seed=52)
+    kw, kb, vw, vb = _branch_params(D, 53)
+    ref = O.two_scale_branch(q, frames, mask, kw, kb, vw, vb)
+    fc, lc, qc = _cuda(frames, lengths, q)
+    clips = ops.downsample_clips(fc, lc)
+    pb, ps, _ = ops.build_proposals(clips)
+    qn, _ = ops.normalize_rows(qc)
+    s_clip, k_clip = ops.clip_score_f32(qn, clips, ps)
+    key, val = F.linear(frames, kw, kb).cuda(), F.linear(frames, vw, vb).cuda()
+    tf, tb = ops.frame_attn_table(key, val, clips, lc)
+    fused, fr = ops.frame_fuse(qn, tf, s_clip, k_clip, 0.7, 0.3, 1.0, want_frame=True)
+    assert (s_clip.cpu() - ref["clip"]).abs().max() <= FP32_TOL
+    same = k_clip.cpu().long() == ref["key_clip"]
+    assert same.float().mean() > 0.999
+    assert (fr.cpu()[same] - ref["frame"][same]).abs().max() <= 5e-6
+    assert (fused.cpu()[same] - ref["branch"][same]).abs().max() <= 5e-6
+
+
+def test_fuse_scores_bit_exact(ops):
+    g = torch.Generator().manual_seed(61)
+    a, b = torch.randn(1000, 37, generator=g), torch.randn(1000, 37, generator=g)
+    ac, bc = _cuda(a, b)
+    got = ops.fuse_scores(ac, bc, 0.7, 0.3).cpu().numpy()
+    ref = O.fuse_branches(a.numpy(), b.numpy())
+    assert np.array_equal(got, ref)  # numpy rounding order of method/eval.py:254, bit exact
+
+
+@pytest.mark.parametrize("M,Nv,K", [(33, 2179, 100), (5, 40, 100), (17, 1000, 128), (3, 5000, 256)])
+def test_topk(ops, M, Nv, K):
+    g = torch.Generator().manual_seed(71)
+    s = torch.randn(M, Nv, generator=g)
+    s[:, ::7] = s[:, 3:4]  # many exact ties: lower id must win
+    (sc,) = _cuda(s)
+    ts, ti = ops.topk(sc, K, id_base=1000)
+    ref = O.topk_ids(s.numpy(), K)
+    kk = min(K, Nv)
+    assert np.array_equal(ti.cpu().numpy()[:, :kk] - 1000, ref[:, :kk])
+    assert np.array_equal(ts.cpu().numpy()[:, :kk], np.take_along_axis(s.numpy(), ref[:, :kk], 1))
+    if K > Nv:
+        assert (ti.cpu()[:, Nv:] == -1).all()
+
+
+def test_merge_topk_equals_global_topk(ops):
+    g = torch.Generator().manual_seed(81)
+    M, Nv, K, G = 21, 1200, 100, 4
+    s = torch.randn(M, Nv, generator=g)
+    s[:, 5::11] = 0.25
+    (sc,) = _cuda(s)
+    shard = Nv // G
+    ls, li = [], []
+    for r in range(G):
+        part = sc[:, r * shard:(r + 1) * shard].contiguous()
+        a, b = ops.topk(part, K, id_base=r * shard)
+        ls.append(a)
+        li.append(b)
+    ms, mi = ops.merge_topk(torch.stack(ls), torch.stack(li))
+    gs, gi = ops.topk(sc, K)
+    assert torch.equal(mi, gi) and torch.equal(ms, gs)
+    assert np.array_equal(gi.cpu().numpy(), O.topk_ids(s.numpy(), K))
+
+
+def test_rank_of_gt_and_recall(ops):
+    g = torch.Generator().manual_seed(91)
+    M, Nv = 64, 300
+    s = torch.randn(M, Nv, generator=g)
+    s[:, 10] = s[:, 20]
+    gts = {i: ([i % Nv] if i % 3 else [i % Nv, (i * 7) % Nv]) for i in range(M)}
+    ptr = np.zeros(M + 1, np.int32)
+    ids = []
+    for i in range(M):
+        ids += gts[i]
+        ptr[i + 1] = len(ids)
+    sc = s.cuda()
+    r = ops.rank_of_gt(sc, torch.from_numpy(ptr).cuda(), torch.tensor(ids, dtype=torch.int32).cuda())
+    ref = O.gt_ranks(-s.numpy(), gts, stable=True)
+    assert np.array_equal(r.cpu().numpy(), ref)
+
+
+def test_candidate_rescoring_plumbing(ops):
+    """candidates -> CSR -> exact clip score per entry -> frame fuse per entry -> sort == dense exact path."""
+    Nv, L, D, M, K = 40, 128, 64, 30, 16
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=101)
+    q = synth.encoded_queries(M, D, seed=102)
+    kw, kb, vw, vb = _branch_params(D, 103)
+    fc, lc, qc = _cuda(frames, lengths, q)
+    clips = ops.downsample_clips(fc, lc)
+    _, ps, _ = ops.build_proposals(clips, want_bf16=False)
+    qn, _ = ops.normalize_rows(qc)
+    s_clip, k_clip = ops.clip_score_f32(qn, clips, ps)
+    tf, _ = ops.frame_attn_table(F.linear(frames, kw, kb).cuda(), F.linear(frames, vw, vb).cuda(), clips, lc,
+                                 want_bf16=False)
+    fused, _ = ops.frame_fuse(qn, tf, s_clip, k_clip, 0.7, 0.3, 1.0)
+    ts, ti = ops.topk(fused, K)
+    # perturb candidate order, then rescore
+    perm = torch.randperm(K)
+    cand = ti[:, perm].contiguous()
+    vid_ptr, q_list, slot = ops.candidates_to_csr(cand, Nv)
+    cs, ck = ops.clip_score_f32(qn, clips, ps, csr=(vid_ptr, q_list))
+    cand_scores = torch.zeros(M, K, device="cuda")
+    ops.frame_fuse_csr(qn, tf, cs, ck, (vid_ptr, q_list, slot), 0.7, 0.3, 1.0, cand_scores, False)
+    rs, ri = ops.sort_candidates(cand_scores, cand, K)
+    assert torch.equal(ri, ti)
+    assert torch.equal(rs, ts)

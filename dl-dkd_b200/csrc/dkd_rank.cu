@@ -206,6 +206,17 @@ __global__ void cand_fill_kernel(const int32_t* __restrict__ cand, int64_t total
   }
 }
 
+// out[slot[e]] = fl(wa * a[e]) + fl(wb * b[e])  (b may be null: out[slot[e]] = a[e])
+__global__ void scatter_fuse_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
+                                    const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
+                                    float* __restrict__ out) {
+  const int64_t total = *total_ptr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = b ? __fadd_rn(__fmul_rn(wa, a[i]), __fmul_rn(wb, b[i])) : a[i];
+    out[slot[i]] = v;
+  }
+}
+
 }  // namespace dkd
 
 using namespace dkd;
@@ -284,6 +295,17 @@ extern "C" int dkd_candidates_to_csr(const int32_t* cand_ids, int32_t M, int32_t
   cand_scan_kernel<<<1, 1024, 0, st>>>(counts, Nv, vid_ptr);
   DKD_LAUNCH_CHECK();
   cand_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand_ids, total, K, Nv, id_base, counts, vid_ptr, q_list, slot);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_scatter_fuse(const float* a, const float* b, float wa, float wb, const int32_t* slot,
+                                const int32_t* vid_ptr, int32_t Nv, int64_t max_entries, float* out, void* stream) {
+  if (!a || !slot || !vid_ptr || !out || Nv <= 0 || max_entries < 0) return DKD_ERR_ARG;
+  if (max_entries == 0) return DKD_OK;
+  int64_t blocks = (max_entries + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scatter_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, wa, wb, slot, vid_ptr + Nv, out);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -1,0 +1,224 @@
+"""Scoring engine: prepared corpus (resident in HBM) + per-query-batch scoring and ranking.
+
+Two scoring heads
+  "frame"      the head the reference ships: max over frames of cos(q, frame), masked
+               (DLDKD.get_sim_scores, method/model.py:307-329), per branch; 0.7/0.3 fusion
+               (method/eval.py:254).
+  "two_scale"  the head north_star names: clip-scale max over the 528 clip
+               proposals + key-clip-guided frame-scale score, w_clip/w_frame per branch, then 0.7/0.3.
+Two precisions
+  "exact"      fp32 SIMT kernels end to end (drop-in parity path).
+  "bf16"       tcgen05 bf16 GEMM for the dense contraction (the hot kernel), approximate fused
+               scores (<= 1e-3 abs), per-query top-Kc candidates re-scored by the exact fp32 kernels,
+               so the returned top-K (ids, scores) equal the exact path's.
+
+HBM layout per branch (Nv videos, L frames, D features, T clips, P = T(T+1)/2 proposals):
+  frames_n   (Nv, L, D) fp32   L2-normalised frames          frame head, exact
+  frames_b   (Nv*L, D)  bf16   same, GEMM B operand          frame head, bf16
+  clips      (Nv, T, D) fp32   downsampled clips             two-scale, exact + rescoring
+  prop_scale (Nv, P)    fp32   1/(w*||mean||)                two-scale, exact + rescoring
+  prop_b     (Nv*P, D)  bf16   L2-normalised proposals       two-scale GEMM B operand
+  table_f    (Nv, P, D) fp32   normalised attention outputs  frame-scale, exact + rescoring
+  table_b    (Nv, P, D) bf16   same                          frame-scale, bf16
+TVR shape, both branches: 2 x (428 + 214 + 107 + 5 + 884 + 1767 + 884 MB) = 8.6 GB of 180 GB.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+BRANCH_WEIGHTS = (0.7, 0.3)  # inheritance, exploration: method/eval.py:254
+
+
+@dataclass
+class BranchData:
+    frames_n: Optional[torch.Tensor] = None
+    frames_b: Optional[torch.Tensor] = None
+    clips: Optional[torch.Tensor] = None
+    prop_scale: Optional[torch.Tensor] = None
+    prop_b: Optional[torch.Tensor] = None
+    table_f: Optional[torch.Tensor] = None
+    table_b: Optional[torch.Tensor] = None
+
+
+@dataclass
+class PreparedCorpus:
+    Nv: int
+    L: int
+    D: int
+    T: int
+    id_base: int
+    mask_u8: torch.Tensor          # (Nv, L)
+    lengths: torch.Tensor          # (Nv,) int32
+    branches: List[BranchData] = field(default_factory=list)
+    heads: tuple = ("frame", "two_scale")
+
+    @property
+    def P(self):
+        return ops.num_proposals(self.T)
+
+    def nbytes(self):
+        tot = 0
+        for b in self.branches:
+            for t in vars(b).values():
+                if t is not None:
+                    tot += t.numel() * t.element_size()
+        return tot
+
+
+def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, heads=("frame", "two_scale"),
+                   precisions=("exact", "bf16"), id_base=0) -> PreparedCorpus:
+    """Query-independent corpus preparation (run once; hoists the per-call F.normalize of
+    method/model.py:319 and builds the two-scale operands).
+
+    frames_by_branch: list of (Nv, L, D) fp32 CUDA tensors from encode_context (1 or 2 branches).
+    mask: (Nv, L) {0,1}.  attn_params: per branch (key_w, key_b, val_w, val_b) of the key-clip
+    attention (needed for the two_scale head).
+    """
+    f0 = frames_by_branch[0]
+    Nv, L, D = f0.shape
+    mask = mask.to(f0.device)
+    mask_u8 = (mask > 0).to(torch.uint8).contiguous()
+    lengths = mask_u8.sum(dim=1).to(torch.int32).contiguous()
+    pc = PreparedCorpus(Nv=Nv, L=L, D=D, T=T, id_base=id_base, mask_u8=mask_u8, lengths=lengths, heads=tuple(heads))
+    for bi, fr in enumerate(frames_by_branch):
+        fr = fr.contiguous().float()
+        bd = BranchData()
+        if "frame" in heads:
+            fn, fb = ops.normalize_rows(fr, want_f32="exact" in precisions or "bf16" in precisions,
+                                        want_bf16="bf16" in precisions)
+            bd.frames_n = None if fn is None else fn.view(Nv, L, D)
+            bd.frames_b = fb
+        if "two_scale" in heads:
+            if attn_params is None:
+                raise ValueError("two_scale head needs the key/value projections (attn_params)")
+            kw, kb, vw, vb = attn_params[bi]
+            bd.clips = ops.downsample_clips(fr, lengths, T)
+            pb, ps, _ = ops.build_proposals(bd.clips, want_bf16="bf16" in precisions, want_scale=True)
+            bd.prop_b = None if pb is None else pb.view(-1, D)
+            bd.prop_scale = ps
+            # W_k / W_v projections: plain library GEMMs in corpus preparation
+            key = F.linear(fr, kw, kb).contiguous()
+            val = F.linear(fr, vw, vb).contiguous()
+            bd.table_f, bd.table_b = ops.frame_attn_table(key, val, bd.clips, lengths, want_f32=True,
+                                                          want_bf16="bf16" in precisions)
+            del key, val
+        pc.branches.append(bd)
+    return pc
+
+
+@dataclass
+class PreparedQueries:
+    M: int
+    Mpad: int
+    qn: List[torch.Tensor]   # per branch (M, D) fp32 normalised
+    qb: List[torch.Tensor]   # per branch (Mpad, D) bf16 normalised (or None)
+
+
+def prepare_queries(q_by_branch, want_bf16=True) -> PreparedQueries:
+    M = q_by_branch[0].shape[0]
+    Mpad = ops.round_up(max(M, 1), 128)
+    qn, qb = [], []
+    for q in q_by_branch:
+        f, b = ops.normalize_rows(q.contiguous().float(), want_f32=True, want_bf16=want_bf16, rows_pad=Mpad)
+        qn.append(f[:M])
+        qb.append(b)
+    return PreparedQueries(M=M, Mpad=Mpad, qn=qn, qb=qb)
+
+
+def _branch_weights(nb):
+    return BRANCH_WEIGHTS[:nb] if nb == 2 else (1.0,)
+
+
+def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", want_arg=False):
+    """Per-branch dense (M, Nv) scores of the reference head. Returns list of (scores, argmax)."""
+    out = []
+    for bd, qn, qb in zip(pc.branches, pq.qn, pq.qb):
+        if precision == "exact":
+            s, a, _ = ops.score_max_f32(qn, bd.frames_n, pc.mask_u8)
+        else:
+            s, a = ops.score_max_bf16(qb, pq.M, bd.frames_b, pc.Nv, pc.L, pc.mask_u8)
+        out.append((s, a))
+    return out
+
+
+def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", w_clip=0.7, w_frame=0.3,
+                         want_frame=False):
+    """Returns (fused (M, Nv), per-branch list of dict(clip, key_clip, frame|None))."""
+    nb = len(pc.branches)
+    wbs = _branch_weights(nb)
+    fused = None
+    per = []
+    for bi, (bd, qn, qb) in enumerate(zip(pc.branches, pq.qn, pq.qb)):
+        if precision == "exact":
+            s_clip, k_clip = ops.clip_score_f32(qn, bd.clips, bd.prop_scale)
+            q, tab = qn, bd.table_f
+        else:
+            s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
+            q, tab = qb, bd.table_b
+        wb = wbs[bi] if nb == 2 else 1.0
+        fused, fr = ops.frame_fuse(q, tab, s_clip, k_clip, w_clip, w_frame, wb, fused=fused, accumulate=bi > 0,
+                                   want_frame=want_frame)
+        per.append(dict(clip=s_clip, key_clip=k_clip, frame=fr))
+    return fused, per
+
+
+def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", precision="bf16", rescore=True,
+         Kc=128, w_clip=0.7, w_frame=0.3):
+    """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score.
+
+    precision="bf16" + rescore: bf16 GEMM scores pick Kc >= K candidates per query, the exact fp32
+    kernels re-score them, the K best survive — identical to precision="exact" unless the true
+    top-K leaks out of the approximate top-Kc (bounded by the 1e-3 bf16 error).
+    """
+    nb = len(pc.branches)
+    wbs = _branch_weights(nb)
+    if head == "frame":
+        sc = score_frame_head(pc, pq, precision)
+        fused = sc[0][0] if nb == 1 else ops.fuse_scores(sc[0][0], sc[1][0], wbs[0], wbs[1])
+    else:
+        fused, _ = score_two_scale_head(pc, pq, precision, w_clip, w_frame)
+    if precision == "exact" or not rescore:
+        return ops.topk(fused, K, pc.id_base)
+    Kc = max(Kc, K)
+    _, cand = ops.topk(fused, Kc, pc.id_base)
+    csr = ops.candidates_to_csr(cand, pc.Nv, pc.id_base)
+    cand_scores = torch.full((pq.M, Kc), float("-inf"), dtype=torch.float32, device=cand.device)
+    if head == "frame":
+        ex = [ops.score_max_f32(qn, bd.frames_n, pc.mask_u8, csr=csr[:2])[0] for bd, qn in zip(pc.branches, pq.qn)]
+        if nb == 2:
+            ops.scatter_fuse(ex[0], ex[1], wbs[0], wbs[1], csr, cand_scores)
+        else:
+            ops.scatter_fuse(ex[0], None, 1.0, 0.0, csr, cand_scores)
+    else:
+        for bi, (bd, qn) in enumerate(zip(pc.branches, pq.qn)):
+            cs, ck = ops.clip_score_f32(qn, bd.clips, bd.prop_scale, csr=csr[:2])
+            wb = wbs[bi] if nb == 2 else 1.0
+            ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
+    return ops.sort_candidates(cand_scores, cand, K)
+
+
+def shard_range(Nv: int, rank_: int, world: int):
+    """Contiguous video shard [lo, hi) of rank_."""
+    per = (Nv + world - 1) // world
+    lo = min(rank_ * per, Nv)
+    return lo, min(lo + per, Nv)
+
+
+def merge_shards(local_scores, local_ids, group=None, merge_fn=None):
+    """All-gather every rank's per-query local top-K (NCCL over NVLink on the GPU box) and merge to
+    the global top-K with dkd_merge_topk.  merge_fn overrides the merge kernel (CPU gloo tests)."""
+    import torch.distributed as dist
+    merge_fn = merge_fn or ops.merge_topk
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_scores, local_ids
+    M, K = local_scores.shape
+    gs = torch.empty((world, M, K), dtype=torch.float32, device=local_scores.device)
+    gi = torch.empty((world, M, K), dtype=torch.int32, device=local_scores.device)
+    dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
+    return merge_fn(gs, gi)

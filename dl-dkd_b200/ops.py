@@ -252,3 +252,12 @@ def sort_candidates(cand_scores, cand_ids, K_out):
     oi = torch.empty((M, K_out), dtype=torch.int32, device=cand_ids.device)
     _lib.call("dkd_sort_candidates", _p(cand_scores), _p(cand_ids), M, K, K_out, _p(os_), _p(oi), _stream())
     return os_, oi
+
+
+def scatter_fuse(a, b, wa, wb, csr, cand_scores):
+    """cand_scores.flat[slot[e]] = fl(wa*a[e]) + fl(wb*b[e]) over the CSR entries (b may be None)."""
+    vid_ptr, q_list, slot = csr
+    _chk(a, torch.float32, "a")
+    _lib.call("dkd_scatter_fuse", _p(a), _p(b), wa, wb, _p(slot), _p(vid_ptr), vid_ptr.numel() - 1, a.numel(),
+              _p(cand_scores), _stream())
+    return cand_scores

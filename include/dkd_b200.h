@@ -173,6 +173,10 @@ int dkd_frame_fuse_csr(const float* q, const float* table, const float* clip_sco
                        const int32_t* slot, int32_t Nv, int32_t P, int32_t D, float w_clip,
                        float w_frame, float w_branch, int32_t accumulate, float* cand_scores,
                        void* stream);
+/* Per-CSR-entry fusion + scatter (reference frame path rescoring): out[slot[e]] =
+ * fl(wa*a[e]) + fl(wb*b[e]) for e < vid_ptr[Nv] (b == NULL: plain scatter of a). */
+int dkd_scatter_fuse(const float* a, const float* b, float wa, float wb, const int32_t* slot,
+                     const int32_t* vid_ptr, int32_t Nv, int64_t max_entries, float* out, void* stream);
 /* Sort each query's K candidates (score desc, id asc) and keep the first K_out. */
 int dkd_sort_candidates(const float* cand_scores, const int32_t* cand_ids, int32_t M, int32_t K,
                         int32_t K_out, float* out_scores, int32_t* out_ids, void* stream);

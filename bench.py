@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — query-video pairs scored+ranked per second on the TVR-shaped synthetic eval.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload tvr_two_scale]
+
+One "step" = one pass of the hot path over the whole query set: encoded query vectors (resident in
+HBM) -> L2-normalise/bf16 cast -> tcgen05 scoring GEMM with fused max/argmax (both branches) ->
+frame-scale gather + fusion -> warp top-128 -> exact fp32 rescoring -> per-query top-100
+[-> NCCL all-gather + merge for N > 1].  The corpus is prepared once (untimed, reported as
+`prep_ms`).  Prints ONE JSON line on rank 0.
+
+Workloads (BASELINE.json configs[1]): TVR shape, 2,179 videos x 128 frames x 3072-d, 10,895 queries
+x <=30 words x 768-d, random-init DL-DKD++ (hidden 384, two branches), synthetic features.
+  tvr_two_scale  north_star head (clip proposals + key-clip frame attention)        [default, headline]
+  tvr_frame      the head the reference ships (max over frames), same kernels
+N > 1: weak scaling — every rank owns its own 2,179-video shard of an N x 2,179-video corpus,
+queries replicated, local top-100 merged through one NCCL all-gather.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TVR = dict(Nv=2179, L=128, Dv=3072, Nq=10895, Lq=30, Dq=768, H=384, T=32)
+K_TOP = 100
+K_CAND = 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def model_config(shape):
+    from oracle.ref_shim import model_config as mc, options
+    cfg = mc(shape["Dv"], shape["Dq"], hidden=shape["H"], n_heads=4, max_ctx_l=shape["L"], max_desc_l=shape["Lq"])
+    return cfg, options()
+
+
+def synth_encoded(shape, device, shard_seed, dkd_model_cls):
+    """Synthetic raw features of the named shapes -> random-init DL-DKD++ encoders (PyTorch) -> encoded
+    frames per branch + mask, encoded query vectors per branch.  Setup only (untimed)."""
+    cfg, opt = model_config(shape)
+    torch.manual_seed(0)
+    model = dkd_model_cls(cfg, opt).to(device).eval()
+    Nv, L, Dv, Nq, Lq, Dq = (shape[k] for k in ("Nv", "L", "Dv", "Nq", "Lq", "Dq"))
+    g = torch.Generator(device=device).manual_seed(1000 + shard_seed)
+    inher, explore = [], []
+    mask = torch.ones(Nv, L, device=device)  # "x 128 frames" headline: every video has all 128 frames
+    with torch.no_grad():
+        for lo in range(0, Nv, 200):  # eval_context_bsz = 200 (method/config.py:48)
+            n = min(200, Nv - lo)
+            x = torch.randn(n, L, Dv, device=device, generator=g)
+            x = x / (x.norm(dim=-1, keepdim=True) + 1e-5)          # l2_normalize_np_array, data_provider.py:71
+            a, b = model.encode_context(x, mask[lo: lo + n])
+            inher.append(a)
+            explore.append(b)
+        gq = torch.Generator(device=device).manual_seed(5_000_000)  # queries identical on every rank
+        qlen = torch.randint(5, Lq + 1, (Nq,), device=device, generator=gq)
+        qi, qe = [], []
+        for lo in range(0, Nq, 500):
+            n = min(500, Nq - lo)
+            x = torch.randn(n, Lq, Dq, device=device, generator=gq)
+            x = x / (x.norm(dim=-1, keepdim=True) + 1e-5)
+            qm = (torch.arange(Lq, device=device)[None] < qlen[lo: lo + n, None]).float()
+            x = x * qm[:, :, None]
+            a, b = model.encode_query(x, qm)
+            qi.append(a)
+            qe.append(b)
+    return model, [torch.cat(inher), torch.cat(explore)], mask, [torch.cat(qi), torch.cat(qe)]
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cpu_baseline(shape, workload, sample_queries, threads=None):
+    """The oracle port of the reference's CPU eval loop on a bounded sample of the same workload:
+    `sample_queries` queries x the full corpus, all host threads.  Returns dict for the JSON line."""
+    from oracle import oracle as O
+    from dkd_b200.model import DLDKD
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    dev = torch.device("cpu")
+    sub = dict(shape)
+    sub["Nq"] = sample_queries
+    t_setup = time.perf_counter()
+    model, frames, mask, qs = synth_encoded(sub, dev, 0, DLDKD)
+    with torch.no_grad():
+        if workload == "tvr_two_scale":
+            lengths = mask.sum(1).long()
+            props, keys, vals = [], [], []
+            for f, (kw, kb, vw, vb) in zip(frames, model.attention_params()):
+                props.append(O.build_proposals(O.downsample_clips(f, lengths, shape["T"])))
+                keys.append(torch.nn.functional.linear(f, kw, kb))
+                vals.append(torch.nn.functional.linear(f, vw, vb))
+            t_setup = time.perf_counter() - t_setup
+            t0 = time.perf_counter()
+            O.cpu_eval_two_scale(qs, props, keys, vals, mask, bsz=50, K=K_TOP)
+            dt = time.perf_counter() - t0
+        else:
+            t_setup = time.perf_counter() - t_setup
+            t0 = time.perf_counter()
+            O.cpu_eval_frame_head(qs, frames, mask, bsz=50, K=K_TOP)
+            dt = time.perf_counter() - t0
+    pairs = sample_queries * shape["Nv"]
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_queries} queries x {shape['Nv']} videos ({workload}, oracle/oracle.py "
+                      f"cpu_eval loop, batches of 50, torch {torch.__version__} CPU, {dt:.1f} s)",
+            "seconds": dt}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dkd_b200", choices=["dkd_b200", "reference"])
+    ap.add_argument("--workload", default="tvr_two_scale", choices=["tvr_two_scale", "tvr_frame"])
+    ap.add_argument("--cpu-sample-queries", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
+    args = ap.parse_args()
+    if args.impl == "dkd_b200" and not args.profile:
+        args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    shape = dict(TVR)
+    head = "two_scale" if args.workload == "tvr_two_scale" else "frame"
+    cfg_common = {"workload": args.workload, "videos_per_gpu": shape["Nv"], "frames": shape["L"],
+                  "visual_dim": shape["Dv"], "queries": shape["Nq"], "hidden": shape["H"], "branches": 2,
+                  "top_k": K_TOP, "l2": "inputs larger than L2 (bf16 corpus operand 884 MB/branch)"}
+
+    import __graft_entry__ as ge
+    ge.load_package()
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
+        vals = []
+        for _ in range(max(args.warmup, 0)):
+            run_cpu_baseline(shape, args.workload, 50)
+        last = None
+        for _ in range(max(args.steps, 1)):
+            last = run_cpu_baseline(shape, args.workload, nq)
+            vals.append(last["value"])
+        v = float(np.mean(vals))
+        sec = float(np.mean([nq * shape["Nv"] / x for x in vals]))
+        line = {"impl": "reference", "metric": "query-video pairs scored+ranked/sec", "value": v, "unit": "pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg_common,
+                "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": last["cores"], "kind": "port",
+                                 "sample": last["sample"]},
+                "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ dkd_b200 arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dkd_b200 import engine, ops, _lib
+    from dkd_b200.model import DLDKD
+    _lib.load()
+
+    model, frames, mask, qs = synth_encoded(shape, dev, rank, DLDKD)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                               T=shape["T"], heads=(head,), id_base=rank * shape["Nv"])
+    e1.record()
+    torch.cuda.synchronize()
+    prep_ms = e0.elapsed_time(e1)
+    del frames
+    qs = [q.contiguous() for q in qs]
+    Nq, Nv = shape["Nq"], shape["Nv"]
+
+    def step(q_dev):
+        pq = engine.prepare_queries(q_dev)
+        s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision="bf16", rescore=True, Kc=K_CAND)
+        if world > 1:
+            s, i = engine.merge_shards(s, i)
+        return s, i
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also: one pass to count kernel launches per step)
+    for _ in range(args.warmup):
+        step(qs)
+    _lib.reset_counters()
+    step(qs)
+    launches_per_step = _lib.launch_count()
+    barrier()
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.set_timed({"dkd_score_max_bf16"})
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        top_s, top_i = step(qs)
+    ev[1].record()
+    barrier()
+    clocks = sampler.result()
+    ms_total = ev[0].elapsed_time(ev[1])
+    gemm_ms = _lib.timed_results().get("dkd_score_max_bf16", [])
+    _lib.set_timed(set())
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pairs_step = Nq * Nv * world
+    value = pairs_step / (ms_step * 1e-3)
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "value": value}))
+        return
+    # ---- e2e: host buffers in, host buffers out, through the same public entry (engine.rank)
+    q_host = [q.cpu().pin_memory() for q in qs]
+    out_s = torch.empty((Nq, K_TOP), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((Nq, K_TOP), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        qd = [q.to(dev, non_blocking=True) for q in q_host]
+        s, i = step(qd)
+        out_s.copy_(s, non_blocking=True)
+        out_i.copy_(i, non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    ev2[1].record()
+    barrier()
+    e2e_ms = ev2[0].elapsed_time(ev2[1]) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": pairs_step / (e2e_ms * 1e-3), "unit": "pairs/s",
+           "h2d_bytes_per_step": int(sum(q.numel() * 4 for q in q_host)),
+           "d2h_bytes_per_step": int(out_s.numel() * 4 + out_i.numel() * 4), "ms_per_step": e2e_ms,
+           "boundary": "encoded query vectors in pinned host memory -> engine.rank -> top-100 (score, id) in host memory"}
+
+    # ---- parity of the timed result: bf16+rescore top-100 == exact fp32 path top-100 (first 512 queries)
+    nchk = 512
+    pq_chk = engine.prepare_queries([q[:nchk] for q in qs])
+    s_ex, i_ex = engine.rank(pc, pq_chk, K=K_TOP, head=head, precision="exact")
+    if world > 1:
+        s_ex, i_ex = engine.merge_shards(s_ex, i_ex)
+    parity = {"queries_checked": nchk,
+              "top100_ids_identical_to_exact_fp32": bool(torch.equal(i_ex, top_i[:nchk])),
+              "top100_scores_identical": bool(torch.equal(s_ex, top_s[:nchk]))}
+
+    if rank == 0:
+        pk = peaks()
+        P = ops.num_proposals(shape["T"])
+        R = P if head == "two_scale" else shape["L"]
+        flops_launch = 2.0 * Nq * Nv * R * shape["H"]
+        gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
+        achieved = flops_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_avg_ms else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        roofline = {"bound": "tensor", "kernel": "score_max_bf16_kernel (tcgen05 GEMM + fused max/argmax)",
+                    "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16_burst"] if achieved else None,
+                    "frac_of_sustained_peak": achieved / pk["bf16_sustained"] if achieved else None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {pk['source']}",
+                    "flops_per_launch": flops_launch, "launches_timed": len(gemm_ms), "avg_launch_ms": gemm_avg_ms,
+                    "share_of_step": (2 * gemm_avg_ms / ms_step) if gemm_avg_ms else None, "traffic": traffic}
+        line = {"metric": "query-video pairs scored+ranked/sec", "value": value, "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": dict(cfg_common, parallelism=f"video-shard x{world}",
+                                                    candidates=K_CAND, rescoring="exact fp32"),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
+                "corpus_bytes": pc.nbytes(), "parity": parity}
+        if not args.no_cpu_baseline and world >= 1:
+            nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
+            line["cpu_baseline"] = run_cpu_baseline(shape, args.workload, nq)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

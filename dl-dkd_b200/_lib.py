@@ -69,6 +69,46 @@ def check(code: int, what: str):
         raise DkdError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3}
+_launches = 0
+_timed_names = set()
+_timed_events = {}
+
+
+def reset_counters():
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def set_timed(names):
+    """bench.py: bracket every call of the named entry points with CUDA events on the current stream."""
+    global _timed_names, _timed_events
+    _timed_names = set(names)
+    _timed_events = {n: [] for n in _timed_names}
+
+
+def timed_results():
+    """name -> list of per-call durations in ms (synchronises)."""
+    import torch
+    torch.cuda.synchronize()
+    return {n: [a.elapsed_time(b) for a, b in evs] for n, evs in _timed_events.items()}
+
+
 def call(name: str, *args):
+    global _launches
     lib = load()
-    check(getattr(lib, name)(*args), name)
+    if name in _timed_names:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(getattr(lib, name)(*args), name)
+        b.record()
+        _timed_events[name].append((a, b))
+    else:
+        check(getattr(lib, name)(*args), name)
+    _launches += KERNELS_PER_CALL.get(name, 1)

@@ -55,7 +55,7 @@ def golden_avg_fixed(M):
 
 def golden_tiny_eval(M):
     rm, re_, rd = M
-    Dv, Dq, H, Lc, Lq = 48, 40, 32, 16, 8
+    Dv, Dq, H, Lc, Lq = 48, 40, 64, 16, 8
     Nv, Nq = 9, 23
     cfg = ref_shim.model_config(Dv, Dq, hidden=H, n_heads=4, max_ctx_l=Lc, max_desc_l=Lq)
     opt = ref_shim.options(eval_query_bsz=5, eval_context_bsz=4)

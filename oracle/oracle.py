@@ -223,3 +223,52 @@ def topk_ids(scores, K):
     """Ranked ids per query: score descending, lower id first on exact ties."""
     order = np.argsort(-np.asarray(scores), axis=1, kind="stable")
     return order[:, :K]
+
+
+# ------------------------------------------------------------------- CPU baseline (bench.py only)
+def key_clip_guided_attention_batched(key, val, mask, proposals, key_clip):
+    """Vectorised (bmm) form of key_clip_guided_attention for the timed CPU baseline: same math,
+    no Python loop over videos (how MS-SL runs it in inference)."""
+    Nv = proposals.shape[0]
+    idx = key_clip.T.unsqueeze(-1).expand(-1, -1, proposals.shape[-1])          # (Nv, M, D)
+    pk = torch.gather(proposals, 1, idx)                                          # (Nv, M, D)
+    logits = torch.bmm(pk, key.transpose(1, 2))                                   # (Nv, M, L)
+    logits = mask_logits(logits, mask.unsqueeze(1))
+    a = torch.softmax(logits, dim=-1)
+    return torch.bmm(a, val).transpose(0, 1)                                      # (M, Nv, D)
+
+
+def cpu_eval_two_scale(q_by_branch, proposals_by_branch, key_by_branch, val_by_branch, mask, bsz=50,
+                       w_clip=0.7, w_frame=0.3, K=100):
+    """The two-scale eval loop the way the reference structures its own (method/eval.py:188-216): query
+    batches of `bsz`, per branch the corpus-side normalisation repeated in every call
+    (method/model.py:319), dense einsum + max, attention, cosine; then numpy fusion (:254) and a full
+    argsort ranking per query (:75).  Returns (fused (M, Nv) float32, top-K ids)."""
+    M = q_by_branch[0].shape[0]
+    outs = [[] for _ in q_by_branch]
+    for lo in range(0, M, bsz):
+        for bi, q in enumerate(q_by_branch):
+            qb = q[lo: lo + bsz]
+            s_clip, _, kc = get_sim_scores(qb, proposals_by_branch[bi], None)
+            g = key_clip_guided_attention_batched(key_by_branch[bi], val_by_branch[bi], mask,
+                                                  proposals_by_branch[bi], kc)
+            s_frame = frame_scale_scores(qb, g)
+            outs[bi].append(w_clip * s_clip + w_frame * s_frame)
+    sc = [torch.cat(o, dim=0).numpy() for o in outs]
+    fused = sc[0] if len(sc) == 1 else fuse_branches(sc[0], sc[1])
+    order = np.stack([np.argsort(-fused[i])[:K] for i in range(fused.shape[0])])
+    return fused, order
+
+
+def cpu_eval_frame_head(q_by_branch, frames_by_branch, mask, bsz=50, K=100):
+    """The reference's shipped eval loop (frame head): method/eval.py:188-216, :254, :75."""
+    M = q_by_branch[0].shape[0]
+    outs = [[] for _ in q_by_branch]
+    for lo in range(0, M, bsz):
+        for bi, q in enumerate(q_by_branch):
+            s, _, _ = get_sim_scores(q[lo: lo + bsz], frames_by_branch[bi], mask)
+            outs[bi].append(s)
+    sc = [torch.cat(o, dim=0).numpy() for o in outs]
+    fused = sc[0] if len(sc) == 1 else fuse_branches(sc[0], sc[1])
+    order = np.stack([np.argsort(-fused[i])[:K] for i in range(fused.shape[0])])
+    return fused, order

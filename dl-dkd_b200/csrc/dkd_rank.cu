@@ -206,6 +206,40 @@ __global__ void cand_fill_kernel(const int32_t* __restrict__ cand, int64_t total
   }
 }
 
+// ---- ambiguous-pair selection: pairs (m, n) whose bf16 argmax gap is below tau ------------------
+__global__ void pair_hist_kernel(const float* __restrict__ gap, int M, int Nv, int64_t ld, float tau,
+                                 int32_t* __restrict__ counts) {
+  const int64_t total = (int64_t)M * Nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / Nv), n = (int)(i % Nv);
+    if (gap[(int64_t)m * ld + n] < tau) atomicAdd(&counts[n], 1);
+  }
+}
+__global__ void pair_fill_kernel(const float* __restrict__ gap, int M, int Nv, int64_t ld, float tau,
+                                 int32_t* __restrict__ cursors, const int32_t* __restrict__ vid_ptr,
+                                 int32_t* __restrict__ q_list, int32_t* __restrict__ slot, int64_t cap) {
+  const int64_t total = (int64_t)M * Nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / Nv), n = (int)(i % Nv);
+    if (gap[(int64_t)m * ld + n] < tau) {
+      const int64_t e = (int64_t)vid_ptr[n] + atomicAdd(&cursors[n], 1);
+      if (e < cap) { q_list[e] = m; slot[e] = (int)((int64_t)m * ld + n); }
+    }
+  }
+}
+// out_clip[slot[e]] = cs[e]; out_key[slot[e]] = ck[e]
+__global__ void pair_scatter_kernel(const float* __restrict__ cs, const int32_t* __restrict__ ck,
+                                    const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
+                                    int64_t cap, float* __restrict__ out_clip, int32_t* __restrict__ out_key) {
+  int64_t total = *total_ptr;
+  if (total > cap) total = cap;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int sl = slot[i];
+    out_clip[sl] = cs[i];
+    out_key[sl] = ck[i];
+  }
+}
+
 // out[slot[e]] = fl(wa * a[e]) + fl(wb * b[e])  (b may be null: out[slot[e]] = a[e])
 __global__ void scatter_fuse_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
                                     const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
@@ -306,6 +340,32 @@ extern "C" int dkd_scatter_fuse(const float* a, const float* b, float wa, float 
   int64_t blocks = (max_entries + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   scatter_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, wa, wb, slot, vid_ptr + Nv, out);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int64_t ld, float tau, int64_t cap,
+                                    int32_t* counts, int32_t* vid_ptr, int32_t* q_list, int32_t* slot,
+                                    void* stream) {
+  if (!gap || !counts || !vid_ptr || !q_list || !slot || M < 0 || Nv <= 0 || ld < Nv || cap < 0) return DKD_ERR_ARG;
+  if ((int64_t)M * ld > 0x7fffffffLL) return DKD_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  DKD_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)Nv, st));
+  const int blocks = 148 * 8;
+  pair_hist_kernel<<<blocks, 256, 0, st>>>(gap, M, Nv, ld, tau, counts);
+  DKD_LAUNCH_CHECK();
+  cand_scan_kernel<<<1, 1024, 0, st>>>(counts, Nv, vid_ptr);
+  DKD_LAUNCH_CHECK();
+  pair_fill_kernel<<<blocks, 256, 0, st>>>(gap, M, Nv, ld, tau, counts, vid_ptr, q_list, slot, cap);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_scatter_pairs(const float* cs, const int32_t* ck, const int32_t* slot, const int32_t* vid_ptr,
+                                 int32_t Nv, int64_t cap, float* out_clip, int32_t* out_key, void* stream) {
+  if (!cs || !ck || !slot || !vid_ptr || !out_clip || !out_key || Nv <= 0 || cap < 0) return DKD_ERR_ARG;
+  if (cap == 0) return DKD_OK;
+  pair_scatter_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(cs, ck, slot, vid_ptr + Nv, cap, out_clip, out_key);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -11,8 +11,12 @@
 //   warp 2  : TMA producer for the query tile (A: 128 queries x D, resident for a whole work
 //             item) + TMEM allocation
 //   warp 3  : spare
-//   warps 4-7: epilogue — tcgen05.ld 32x32b, running (max, first-argmax) per query row across
-//             the R / BLOCK_N tiles of one video, direct fp32 / int32 stores.
+//   warps 4-11: epilogue — two warps per TMEM lane quarter, each owning half of the tile's columns
+//             (tcgen05.ld 32x32b.x32/.x16), running top-2 per query row across the R / BLOCK_N tiles
+//             of one video; the column position rides in the 4 low mantissa bits of the score
+//             (LOP3 + 3 FMNMX per element), the 16-column chunk id is tracked once per chunk.
+//             Halves are merged through shared memory; direct fp32 / int32 stores of
+//             (max, first argmax, gap to the runner-up).
 // A work item = (query tile of 128, chunk of kVideoChunk videos); items are ordered query-tile
 // fastest so that CTAs running at the same time stream the same corpus rows out of L2.
 //
@@ -30,7 +34,8 @@ constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxKBlocks = 8;    // D <= 512
 constexpr int kMaxStages = 8;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;
+constexpr int kNumEpiThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -107,6 +112,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Running top-2 of "score with its position-in-chunk in the 4 low mantissa bits".
+struct Top2 {
+  float best, second;
+  int chunk;  // 16-column chunk (within the video) that holds `best`
+};
+constexpr float kNegHuge = -3.0e38f;
+
+// one 16-column chunk: r[0..15] raw fp32 bits, chunk id `cid`
+template <bool kHasMask>
+__device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, const uint8_t* mrow) {
+  const float before = t.best;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t b = r[j];
+    if (kHasMask) {
+      if (__ldg(mrow + j) == 0) b = __float_as_uint(DKD_MASKED_SCORE);
+    }
+    const float u = __uint_as_float((b & 0xfffffff0u) | (uint32_t)(15 - j));
+    t.second = fmaxf(t.second, fminf(t.best, u));
+    t.best = fmaxf(t.best, u);
+  }
+  if (t.best != before) t.chunk = cid;
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (sm_100 version 1).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -130,6 +179,7 @@ struct GemmParams {
   const uint8_t* mask;
   float* out_max;
   int32_t* out_arg;
+  float* out_gap;     // optional: best - runner-up (bf16-level ambiguity of the argmax)
   int64_t ld_out;
 };
 
@@ -139,6 +189,8 @@ struct __align__(8) SmemCtl {
   uint64_t a_full, a_empty;
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  float2 xchg[2][128];  // half-1 -> half-0 epilogue exchange (best, second), double buffered
+  int xchg_chunk[2][128];
 };
 
 template <bool kHasMask>
@@ -164,7 +216,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int i = 0; i < p.stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
     mbar_init(&ctl->a_full, 1);
     mbar_init(&ctl->a_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], kNumEpiThreads); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_x); }
@@ -253,42 +305,74 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;             // column half of every tile
     const int row_in_tile = quarter * 32 + lane;
+    const int chunks = p.block_n >> 4;
+    const int c_lo = half == 0 ? 0 : ((chunks + 1) >> 1);            // first 16-col chunk of this half
+    const int c_hi = half == 0 ? ((chunks + 1) >> 1) : chunks;       // one past the last
     uint32_t tile_ctr = 0;
+    uint32_t vctr = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int q_tile = item % num_q_tiles;
       const int vchunk = item / num_q_tiles;
       const int v0 = vchunk * p.video_chunk;
       const int v1 = min(v0 + p.video_chunk, p.Nv);
       const int m = q_tile * kBlockM + row_in_tile;
-      for (int v = v0; v < v1; ++v) {
-        float best = -INFINITY;
-        int besti = 0;
+      for (int v = v0; v < v1; ++v, ++vctr) {
+        Top2 t2;
+        t2.best = kNegHuge; t2.second = kNegHuge; t2.chunk = 0;
+        const uint8_t* mvid = kHasMask ? p.mask + (int64_t)v * p.R : nullptr;
         for (int t = 0; t < tiles_per_video; ++t, ++tile_ctr) {
           const uint32_t as = tile_ctr & 1u;
           const uint32_t aphase = (tile_ctr >> 1) & 1u;
           mbar_wait(&ctl->tmem_full[as], aphase);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)p.block_n;
-          for (int c = 0; c < p.block_n; c += 16) {
-            float vals[16];
-            tmem_ld16(taddr + (uint32_t)c, vals);
-            const int col0 = t * p.block_n + c;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float s = vals[j];
-              if (kHasMask) {
-                if (__ldg(&p.mask[(int64_t)v * p.R + col0 + j]) == 0) s = DKD_MASKED_SCORE;
-              }
-              if (s > best) { best = s; besti = col0 + j; }
-            }
+          const int cid0 = t * chunks;  // chunk id (within the video) of this tile's first chunk
+          int c = c_lo;
+          for (; c + 2 <= c_hi; c += 2) {
+            uint32_t r[32];
+            tmem_ld32_issue(taddr + (uint32_t)(c << 4), r);
+            tmem_ld_wait();
+            top2_chunk<kHasMask>(t2, r, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
+            top2_chunk<kHasMask>(t2, r + 16, cid0 + c + 1, kHasMask ? mvid + ((cid0 + c + 1) << 4) : nullptr);
+          }
+          if (c < c_hi) {
+            uint32_t r[16];
+            tmem_ld16_issue(taddr + (uint32_t)(c << 4), r);
+            tmem_ld_wait();
+            top2_chunk<kHasMask>(t2, r, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
           }
           tc_fence_before();
           mbar_arrive(&ctl->tmem_empty[as]);
         }
-        if (m < p.M) {
-          p.out_max[(int64_t)m * p.ld_out + v] = best;
-          if (p.out_arg) p.out_arg[(int64_t)m * p.ld_out + v] = besti;
+        // merge the two column halves of this query row (named barrier per lane quarter, 64 threads)
+        const int slot = vctr & 1u;
+        if (half == 1) {
+          ctl->xchg[slot][row_in_tile] = make_float2(t2.best, t2.second);
+          ctl->xchg_chunk[slot][row_in_tile] = t2.chunk;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+        if (half == 0) {
+          const float2 o = ctl->xchg[slot][row_in_tile];
+          const int oc = ctl->xchg_chunk[slot][row_in_tile];
+          // candidates in column order within equal scores: compare (value desc, chunk asc)
+          float b = t2.best, s2 = t2.second;
+          int ch = t2.chunk;
+          const bool take = (o.x > b) || (o.x == b && oc < ch);
+          s2 = fmaxf(fmaxf(s2, o.y), take ? b : o.x);
+          if (take) { b = o.x; ch = oc; }
+          if (m < p.M) {
+            const uint32_t bb = __float_as_uint(b);
+            const int idx = (ch << 4) + 15 - (int)(bb & 15u);
+            float val = __uint_as_float((bb & 0xfffffff0u) | 8u);
+            float sec = __uint_as_float((__float_as_uint(s2) & 0xfffffff0u) | 8u);
+            if (val < -0.99e10f) val = DKD_MASKED_SCORE;   // fully masked video: exactly the fill value
+            const int64_t o64 = (int64_t)m * p.ld_out + v;
+            p.out_max[o64] = val;
+            if (p.out_arg) p.out_arg[o64] = idx;
+            if (p.out_gap) p.out_gap[o64] = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
+          }
         }
       }
     }
@@ -347,10 +431,10 @@ using namespace dkd;
 
 extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                                   int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
-                                  int32_t* out_arg, int64_t ld_out, void* stream) {
+                                  int32_t* out_arg, float* out_gap, int64_t ld_out, void* stream) {
   if (!q_bf16 || !x_bf16 || !out_max || M < 0 || Nv < 0 || ld_out < Nv) return DKD_ERR_ARG;
   if (Mpad < M || Mpad % kBlockM != 0) return DKD_ERR_SHAPE;
-  if (R <= 0 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
+  if (R <= 0 || R > 4096 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(x_bf16) & 15)) return DKD_ERR_ALIGN;
   if (M == 0 || Nv == 0) return DKD_OK;
   if ((int64_t)Nv * R > 0x7fffffffLL) return DKD_ERR_SHAPE;
@@ -379,7 +463,7 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
 
   GemmParams p{};
   p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages;
-  p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
+  p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   // videos per work item: enough items for ~all SMs x many waves, >= 1
   const int num_q_tiles = Mpad / kBlockM;
   int vc = 16;

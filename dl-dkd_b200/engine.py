@@ -145,9 +145,17 @@ def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact",
     return out
 
 
+AMBIGUITY_TAU = 1.0e-3  # bf16 argmax gaps below this are re-resolved in fp32 (DESIGN.md "bf16 and the key clip")
+
+
 def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", w_clip=0.7, w_frame=0.3,
-                         want_frame=False):
-    """Returns (fused (M, Nv), per-branch list of dict(clip, key_clip, frame|None))."""
+                         want_frame=False, tau=AMBIGUITY_TAU):
+    """Returns (fused (M, Nv), per-branch list of dict(clip, key_clip, frame|None)).
+
+    precision="bf16": the tcgen05 GEMM also reports, per (query, video), the gap between the best and
+    the runner-up proposal.  The key clip steers the frame-scale term discontinuously, so pairs whose
+    gap is below `tau` (the bf16 noise floor on score differences) get their clip score and key clip
+    recomputed by the exact fp32 kernel before the frame-scale gather; tau=0 disables the pass."""
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
     fused = None
@@ -157,7 +165,13 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
             s_clip, k_clip = ops.clip_score_f32(qn, bd.clips, bd.prop_scale)
             q, tab = qn, bd.table_f
         else:
-            s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
+            if tau > 0:
+                s_clip, k_clip, gap = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P, want_gap=True)
+                csr = ops.select_pairs_csr(gap, tau)
+                cs, ck = ops.clip_score_f32(qn, bd.clips, bd.prop_scale, csr=csr[:2])
+                ops.scatter_pairs(cs, ck, csr, s_clip, k_clip)
+            else:
+                s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
             q, tab = qb, bd.table_b
         wb = wbs[bi] if nb == 2 else 1.0
         fused, fr = ops.frame_fuse(q, tab, s_clip, k_clip, w_clip, w_frame, wb, fused=fused, accumulate=bi > 0,
@@ -167,7 +181,7 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
 
 
 def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", precision="bf16", rescore=True,
-         Kc=128, w_clip=0.7, w_frame=0.3):
+         Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU):
     """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score.
 
     precision="bf16" + rescore: bf16 GEMM scores pick Kc >= K candidates per query, the exact fp32
@@ -180,7 +194,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
         sc = score_frame_head(pc, pq, precision)
         fused = sc[0][0] if nb == 1 else ops.fuse_scores(sc[0][0], sc[1][0], wbs[0], wbs[1])
     else:
-        fused, _ = score_two_scale_head(pc, pq, precision, w_clip, w_frame)
+        fused, _ = score_two_scale_head(pc, pq, precision, w_clip, w_frame, tau=tau)
     if precision == "exact" or not rescore:
         return ops.topk(fused, K, pc.id_base)
     Kc = max(Kc, K)

@@ -124,8 +124,9 @@ def clip_score_f32(qn, clips, prop_scale, csr=None):
     return om, oa
 
 
-def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None):
-    """tcgen05 GEMM + fused max/argmax: q_bf16 (Mpad,D), x_bf16 (Nv*R, D) -> (max (M,Nv), argmax (M,Nv))."""
+def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None, want_gap=False):
+    """tcgen05 GEMM + fused max/argmax: q_bf16 (Mpad,D), x_bf16 (Nv*R, D) -> (max (M,Nv), argmax (M,Nv))
+    [+ gap (M,Nv) = best - runner-up when want_gap]."""
     _chk(q_bf16, torch.bfloat16, "q_bf16")
     _chk(x_bf16, torch.bfloat16, "x_bf16")
     Mpad, D = q_bf16.shape
@@ -136,9 +137,32 @@ def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=No
     dev = q_bf16.device
     om = out_max if out_max is not None else torch.empty((M, Nv), dtype=torch.float32, device=dev)
     oa = out_arg if out_arg is not None else torch.empty((M, Nv), dtype=torch.int32, device=dev)
-    _lib.call("dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D, _p(mask), _p(om), _p(oa), Nv,
+    og = torch.empty((M, Nv), dtype=torch.float32, device=dev) if want_gap else None
+    _lib.call("dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D, _p(mask), _p(om), _p(oa), _p(og), Nv,
               _stream())
-    return om, oa
+    return (om, oa, og) if want_gap else (om, oa)
+
+
+def select_pairs_csr(gap, tau, cap=None):
+    """CSR by video of the pairs whose bf16 argmax gap is below tau -> (vid_ptr, q_list, slot)."""
+    _chk(gap, torch.float32, "gap")
+    M, Nv = gap.shape
+    cap = M * Nv if cap is None else cap
+    dev = gap.device
+    counts = torch.empty((Nv,), dtype=torch.int32, device=dev)
+    vid_ptr = torch.empty((Nv + 1,), dtype=torch.int32, device=dev)
+    q_list = torch.empty((cap,), dtype=torch.int32, device=dev)
+    slot = torch.empty((cap,), dtype=torch.int32, device=dev)
+    _lib.call("dkd_select_pairs_csr", _p(gap), M, Nv, Nv, tau, cap, _p(counts), _p(vid_ptr), _p(q_list), _p(slot),
+              _stream())
+    return vid_ptr, q_list, slot
+
+
+def scatter_pairs(cs, ck, csr, out_clip, out_key):
+    """Write the re-resolved (clip score, key clip) of the CSR entries back into the dense matrices."""
+    vid_ptr, q_list, slot = csr
+    _lib.call("dkd_scatter_pairs", _p(cs), _p(ck), _p(slot), _p(vid_ptr), vid_ptr.numel() - 1, slot.numel(),
+              _p(out_clip), _p(out_key), _stream())
 
 
 def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):

@@ -107,10 +107,23 @@ int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const flo
  * clip-scale contraction of SURVEY §8 N3 (R = P = 528).
  * TMA descriptors are encoded on the host per call (cuTensorMapEncodeTiled fetched through
  * cudaGetDriverEntryPoint) and passed as kernel parameters: no workspace.
+ * out_gap (optional): best score minus the runner-up score of the same (query, video) — pairs whose
+ * gap is below the bf16 noise floor have an ambiguous argmax and are re-resolved in fp32
+ * (dkd_select_pairs_csr -> dkd_clip_score_f32 (CSR) -> dkd_scatter_pairs).  Scores carry the column
+ * position in their 4 low mantissa bits inside the kernel: returned values are exact to 8 ulp.
  */
 int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                        int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
-                       int32_t* out_arg, int64_t ld_out, void* stream);
+                       int32_t* out_arg, float* out_gap, int64_t ld_out, void* stream);
+
+/* Ambiguous-pair bookkeeping: CSR (by video) of all pairs (m, n) with gap[m, n] < tau.
+ * counts (Nv) scratch; vid_ptr (Nv+1); q_list / slot (cap entries; slot = m * ld + n).  Entries beyond
+ * `cap` are dropped (size cap = M * Nv to make that impossible). */
+int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int64_t ld, float tau, int64_t cap,
+                         int32_t* counts, int32_t* vid_ptr, int32_t* q_list, int32_t* slot, void* stream);
+/* out_clip[slot[e]] = cs[e], out_key[slot[e]] = ck[e] for e < min(vid_ptr[Nv], cap). */
+int dkd_scatter_pairs(const float* cs, const int32_t* ck, const int32_t* slot, const int32_t* vid_ptr,
+                      int32_t Nv, int64_t cap, float* out_clip, int32_t* out_key, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Key-clip-guided frame attention, query-independent table form:

@@ -9,6 +9,12 @@ dev = torch.device("cuda")
 
 def stats(pc, pq, tag, K=100):
     f_ex, per_ex = engine.score_two_scale_head(pc, pq, "exact")
+    for tau in (0.0, 2e-4, 5e-4, 1e-3, 2e-3):
+        f_bf, per_bf = engine.score_two_scale_head(pc, pq, "bf16", tau=tau)
+        d = (f_ex - f_bf).abs()
+        fl = [(per_ex[b]["key_clip"] != per_bf[b]["key_clip"]).float().mean().item() for b in range(2)]
+        _, _, gap = ops.score_max_bf16(pq.qb[0], pq.M, pc.branches[0].prop_b, pc.Nv, pc.P, want_gap=True)
+        print(tag, f"tau={tau:g}: flagged {(gap < tau).float().mean().item():.4f}  fused |d| max {d.max().item():.2e} p99.99 {torch.quantile(d.flatten()[:10_000_000], 0.9999).item():.2e}  flips {fl[0]:.5f} {fl[1]:.5f}")
     f_bf, per_bf = engine.score_two_scale_head(pc, pq, "bf16")
     d = (f_ex - f_bf).abs()
     print(tag, "fused |d| max %.2e mean %.2e" % (d.max().item(), d.mean().item()))

@@ -24,6 +24,7 @@
 // one K block = 64 bf16 = 128 B per row, 8-row groups 1024 B apart.
 #include <cuda.h>  // CUtensorMap types only; the encode entry point is fetched at run time
 #include <cstdio>
+#include <cstdlib>
 
 #include "dkd_common.cuh"
 
@@ -33,7 +34,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxKBlocks = 8;    // D <= 512
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kNumThreads = 384;
 constexpr int kNumEpiThreads = 256;
 constexpr int kTmemCols = 512;
@@ -156,6 +157,48 @@ __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, 
   if (t.best != before) t.chunk = cid;
 }
 
+// ---- cluster / CTA-pair helpers (cta_group::2) --------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) inside CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// commit to the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (sm_100 version 1).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -167,8 +210,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__host__ __device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__host__ __device__ __forceinline__ uint32_t make_idesc(int n, int m) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct GemmParams {
@@ -180,6 +223,7 @@ struct GemmParams {
   float* out_max;
   int32_t* out_arg;
   float* out_gap;     // optional: best - runner-up (bf16-level ambiguity of the argmax)
+  int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0
   int64_t ld_out;
 };
 
@@ -193,7 +237,11 @@ struct __align__(8) SmemCtl {
   int xchg_chunk[2][128];
 };
 
-template <bool kHasMask>
+// kCta = 1: one CTA per tile (cta_group::1).  kCta = 2: CTA pair (cluster of 2, cta_group::2): the two CTAs
+// hold different query tiles and each half of the corpus tile; the leader (rank 0) issues M=256 MMAs
+// that read both halves, which halves the shared-memory operand traffic and the L2->SM corpus traffic
+// per CTA and doubles the depth of the corpus ring.
+template <bool kHasMask, int kCta>
 __global__ void __launch_bounds__(kNumThreads, 1)
 score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                       const GemmParams p) {
@@ -201,31 +249,42 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int num_kb = p.D / kBlockK;
   const uint32_t a_kb_bytes = kBlockM * kBlockK * 2;        // 16 KB per K block
-  const uint32_t b_stage_bytes = p.block_n * kBlockK * 2;   // block_n x 128 B
+  const int b_rows = p.block_n / kCta;                      // corpus rows this CTA stages per K block
+  const uint32_t b_stage_bytes = b_rows * kBlockK * 2;      // b_rows x 128 B
+  const uint32_t cta_rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)num_kb * a_kb_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_b + (size_t)p.stages * b_stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_video = p.R / p.block_n;
-  const int num_q_tiles = p.Mpad / kBlockM;
+  const int num_q_tiles = p.Mpad / (kBlockM * kCta);        // query tiles (kCta == 2: tile PAIRS)
   const int num_vchunks = (p.Nv + p.video_chunk - 1) / p.video_chunk;
   const int num_items = num_q_tiles * num_vchunks;
+  const int worker = blockIdx.x / kCta;                     // cluster id
+  const int num_workers = gridDim.x / kCta;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
     mbar_init(&ctl->a_full, 1);
     mbar_init(&ctl->a_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], kNumEpiThreads); }
+    // tmem_empty: one elected arrive per epilogue warp, from both CTAs of a pair
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 8 * kCta); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_x); }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (kCta == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -233,17 +292,24 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // ===== corpus (B) producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = worker; item < num_items; item += num_workers) {
         const int vchunk = item / num_q_tiles;
         const int v0 = vchunk * p.video_chunk;
         const int v1 = min(v0 + p.video_chunk, p.Nv);
         for (int v = v0; v < v1; ++v) {
           for (int t = 0; t < tiles_per_video; ++t) {
-            const int row = v * p.R + t * p.block_n;
+            const int row = (p.debug_flags & 2) ? 0 : v * p.R + t * p.block_n;
             for (int kb = 0; kb < num_kb; ++kb) {
               mbar_wait(&ctl->empty[stage], phase ^ 1);
-              mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
-              tma_load_2d(&map_x, &ctl->full[stage], smem_b + (size_t)stage * b_stage_bytes, kb * kBlockK, row);
+              if (kCta == 1) {
+                mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
+                tma_load_2d(&map_x, &ctl->full[stage], smem_b + (size_t)stage * b_stage_bytes, kb * kBlockK, row);
+              } else {
+                // both halves report to the leader's barrier
+                if (leader) mbar_expect_tx(&ctl->full[stage], 2 * b_stage_bytes);
+                tma_load_2d_pair(&map_x, mapa_u32(smem_u32(&ctl->full[stage]), 0), smem_b + (size_t)stage * b_stage_bytes,
+                                 kb * kBlockK, row + (int)cta_rank * b_rows);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -254,23 +320,30 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // ===== query tile (A) producer =====
     if (lane == 0) {
       uint32_t iphase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int q_tile = item % num_q_tiles;
+      for (int item = worker; item < num_items; item += num_workers) {
+        const int q_tile = (item % num_q_tiles) * kCta + (int)cta_rank;
         mbar_wait(&ctl->a_empty, iphase ^ 1);
-        mbar_expect_tx(&ctl->a_full, (uint32_t)num_kb * a_kb_bytes);
-        for (int kb = 0; kb < num_kb; ++kb)
-          tma_load_2d(&map_q, &ctl->a_full, smem_a + (size_t)kb * a_kb_bytes, kb * kBlockK, q_tile * kBlockM);
+        if (kCta == 1) {
+          mbar_expect_tx(&ctl->a_full, (uint32_t)num_kb * a_kb_bytes);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_2d(&map_q, &ctl->a_full, smem_a + (size_t)kb * a_kb_bytes, kb * kBlockK, q_tile * kBlockM);
+        } else {
+          if (leader) mbar_expect_tx(&ctl->a_full, 2u * (uint32_t)num_kb * a_kb_bytes);
+          const uint32_t bar = mapa_u32(smem_u32(&ctl->a_full), 0);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_2d_pair(&map_q, bar, smem_a + (size_t)kb * a_kb_bytes, kb * kBlockK, q_tile * kBlockM);
+        }
         iphase ^= 1;
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.block_n);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc(p.block_n, kBlockM * kCta);
       int stage = 0; uint32_t phase = 0;
       uint32_t iphase = 0;
       uint32_t tile_ctr = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = worker; item < num_items; item += num_workers) {
         const int vchunk = item / num_q_tiles;
         const int v0 = vchunk * p.video_chunk;
         const int v1 = min(v0 + p.video_chunk, p.Nv);
@@ -292,14 +365,15 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in 16-byte units
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              if (kCta == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
             }
-            umma_commit(&ctl->empty[stage]);
+            if (kCta == 1) umma_commit(&ctl->empty[stage]); else umma_commit_pair(&ctl->empty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&ctl->tmem_full[as]);
+          if (kCta == 1) umma_commit(&ctl->tmem_full[as]); else umma_commit_pair(&ctl->tmem_full[as]);
         }
-        umma_commit(&ctl->a_empty);
+        if (kCta == 1) umma_commit(&ctl->a_empty); else umma_commit_pair(&ctl->a_empty);
       }
     }
   } else if (warp >= 4) {
@@ -312,8 +386,8 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int c_hi = half == 0 ? ((chunks + 1) >> 1) : chunks;       // one past the last
     uint32_t tile_ctr = 0;
     uint32_t vctr = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int q_tile = item % num_q_tiles;
+    for (int item = worker; item < num_items; item += num_workers) {
+      const int q_tile = (item % num_q_tiles) * kCta + (int)cta_rank;
       const int vchunk = item / num_q_tiles;
       const int v0 = vchunk * p.video_chunk;
       const int v1 = min(v0 + p.video_chunk, p.Nv);
@@ -329,7 +403,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)p.block_n;
           const int cid0 = t * chunks;  // chunk id (within the video) of this tile's first chunk
-          int c = c_lo;
+          int c = (p.debug_flags & 1) ? c_hi : c_lo;
           for (; c + 2 <= c_hi; c += 2) {
             uint32_t r[32];
             tmem_ld32_issue(taddr + (uint32_t)(c << 4), r);
@@ -344,7 +418,11 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             top2_chunk<kHasMask>(t2, r, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
           }
           tc_fence_before();
-          mbar_arrive(&ctl->tmem_empty[as]);
+          __syncwarp();
+          if (lane == 0) {
+            if (kCta == 1) mbar_arrive(&ctl->tmem_empty[as]);
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
+          }
         }
         // merge the two column halves of this query row (named barrier per lane quarter, 64 threads)
         const int slot = vctr & 1u;
@@ -379,10 +457,11 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    if (kCta == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 
@@ -429,6 +508,27 @@ static int pick_block_n(int R) {
 
 using namespace dkd;
 
+template <bool kHasMask, int kCta>
+static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const GemmParams& p, int grid,
+                       size_t smem_bytes, cudaStream_t st) {
+  auto kern = score_max_bf16_kernel<kHasMask, kCta>;
+  DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DKD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_q, map_x, p));
+  return DKD_OK;
+}
+
 extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                                   int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
                                   int32_t* out_arg, float* out_gap, int64_t ld_out, void* stream) {
@@ -446,9 +546,14 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
+  // CTA pairs (cta_group::2) whenever the shapes allow: two query tiles per pair, corpus tile split in
+  // halves of a multiple of 8 rows.  DKD_GEMM_CTA=1 forces the single-CTA kernel (A/B measurements).
+  int cta = (Mpad % (2 * kBlockM) == 0 && (block_n / 2) % 8 == 0 && sms >= 2) ? 2 : 1;
+  { const char* e = getenv("DKD_GEMM_CTA"); if (e && atoi(e) == 1) cta = 1; }
+
   const int num_kb = D / kBlockK;
   const size_t a_bytes = (size_t)num_kb * kBlockM * kBlockK * 2;
-  const size_t b_stage = (size_t)block_n * kBlockK * 2;
+  const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2;
   const size_t fixed = a_bytes + sizeof(SmemCtl) + 1024 /* alignment slack */ + 256;
   if ((size_t)max_smem < fixed + 2 * b_stage) return DKD_ERR_SHAPE;
   int stages = (int)(((size_t)max_smem - fixed) / b_stage);
@@ -458,28 +563,25 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
   CUtensorMap map_q, map_x;
   int rc = make_map_2d(&map_q, q_bf16, (uint64_t)Mpad, (uint64_t)D, kBlockM);
   if (rc) return rc;
-  rc = make_map_2d(&map_x, x_bf16, (uint64_t)Nv * R, (uint64_t)D, (uint32_t)block_n);
+  rc = make_map_2d(&map_x, x_bf16, (uint64_t)Nv * R, (uint64_t)D, (uint32_t)(block_n / cta));
   if (rc) return rc;
 
   GemmParams p{};
   p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages;
+  { const char* e = getenv("DKD_GEMM_DEBUG"); p.debug_flags = e ? atoi(e) : 0; }
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
-  // videos per work item: enough items for ~all SMs x many waves, >= 1
-  const int num_q_tiles = Mpad / kBlockM;
+  // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
+  const int num_q_tiles = Mpad / (kBlockM * cta);
+  const int workers = sms / cta;
   int vc = 16;
-  while (vc > 1 && (int64_t)num_q_tiles * ((Nv + vc - 1) / vc) < (int64_t)sms * 8) vc >>= 1;
+  while (vc > 1 && (int64_t)num_q_tiles * ((Nv + vc - 1) / vc) < (int64_t)workers * 8) vc >>= 1;
   p.video_chunk = vc;
   const int64_t num_items = (int64_t)num_q_tiles * ((Nv + vc - 1) / vc);
-  const int grid = (int)(num_items < sms ? num_items : sms);
+  const int grid = (int)(num_items < workers ? num_items : workers) * cta;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (mask) {
-    DKD_CUDA_TRY(cudaFuncSetAttribute(score_max_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    score_max_bf16_kernel<true><<<grid, kNumThreads, smem_bytes, st>>>(map_q, map_x, p);
-  } else {
-    DKD_CUDA_TRY(cudaFuncSetAttribute(score_max_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    score_max_bf16_kernel<false><<<grid, kNumThreads, smem_bytes, st>>>(map_q, map_x, p);
-  }
-  DKD_LAUNCH_CHECK();
-  return DKD_OK;
+  if (cta == 2) return mask ? launch_gemm<true, 2>(map_q, map_x, p, grid, smem_bytes, st)
+                            : launch_gemm<false, 2>(map_q, map_x, p, grid, smem_bytes, st);
+  return mask ? launch_gemm<true, 1>(map_q, map_x, p, grid, smem_bytes, st)
+              : launch_gemm<false, 1>(map_q, map_x, p, grid, smem_bytes, st);
 }

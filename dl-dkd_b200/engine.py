@@ -120,7 +120,7 @@ class PreparedQueries:
 
 def prepare_queries(q_by_branch, want_bf16=True) -> PreparedQueries:
     M = q_by_branch[0].shape[0]
-    Mpad = ops.round_up(max(M, 1), 128)
+    Mpad = ops.round_up(max(M, 1), 256)  # 2 x 128: CTA pairs own two query tiles
     qn, qb = [], []
     for q in q_by_branch:
         f, b = ops.normalize_rows(q.contiguous().float(), want_f32=True, want_bf16=want_bf16, rows_pad=Mpad)

@@ -127,13 +127,15 @@ def test_clip_score_f32(ops, M, Nv, D):
     assert ok, f"{nbad} key-clip mismatches beyond fp32 ties"
 
 
-@pytest.mark.parametrize("M,Nv,R,D,masked", [
-    (200, 37, 528, 384, False),   # clip-proposal shape, two query tiles, ragged M
-    (50, 23, 128, 384, True),     # reference frame path with mask
-    (128, 300, 528, 384, False),  # many work items
-    (10, 4, 64, 128, True),
+@pytest.mark.parametrize("M,pad,Nv,R,D,masked", [
+    (200, 256, 37, 528, 384, False),   # clip-proposal shape, CTA pair (cta_group::2), ragged M
+    (50, 128, 23, 128, 384, True),     # reference frame path with mask, single CTA (cta_group::1)
+    (128, 256, 300, 528, 384, False),  # CTA pair, many work items, second query tile all padding
+    (300, 128, 150, 528, 384, False),  # three query tiles -> single-CTA kernel
+    (700, 256, 61, 128, 384, True),    # CTA pair with mask, three tile pairs
+    (10, 128, 4, 64, 128, True),
 ])
-def test_score_max_bf16(ops, M, Nv, R, D, masked):
+def test_score_max_bf16(ops, M, pad, Nv, R, D, masked):
     g = torch.Generator().manual_seed(77)
     x = torch.randn(Nv, R, D, generator=g) + 0.5 * torch.randn(Nv, 1, D, generator=g)
     q = torch.randn(M, D, generator=g)
@@ -143,11 +145,11 @@ def test_score_max_bf16(ops, M, Nv, R, D, masked):
         mask = (torch.arange(R)[None] < lengths[:, None]).float()
     s_ref, rows_ref, a_ref = O.get_sim_scores(q, x, mask)
     qc, xc = _cuda(q, x)
-    Mpad = ops.round_up(M, 128)
+    Mpad = ops.round_up(M, pad)
     _, qb = ops.normalize_rows(qc, want_f32=False, want_bf16=True, rows_pad=Mpad)
     _, xb = ops.normalize_rows(xc, want_f32=False, want_bf16=True)
     mc = None if mask is None else mask.to(torch.uint8).cuda()
-    om, oa = ops.score_max_bf16(qb, M, xb, Nv, R, mc)
+    om, oa, og = ops.score_max_bf16(qb, M, xb, Nv, R, mc, want_gap=True)
     torch.cuda.synchronize()
     # (1) vs fp32 oracle: north_star tolerance
     assert (om.cpu() - s_ref).abs().max() <= BF16_TOL
@@ -163,6 +165,10 @@ def test_score_max_bf16(ops, M, Nv, R, D, masked):
     # (3) vs oracle argmax: only near ties at bf16 resolution may differ
     ok, nbad = _argmax_ok(oa.cpu(), rows_ref, a_ref, 2 * BF16_TOL)
     assert ok
+    # (4) gap = best - runner-up of the same bf16 operands
+    if R > 1:
+        top2 = torch.topk(rows_b, 2, dim=1).values
+        assert ((top2[:, 0] - top2[:, 1]) - og.cpu()).abs().max() <= 4e-5
 
 
 def _branch_params(D, seed):

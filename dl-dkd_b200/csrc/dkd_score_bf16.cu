@@ -6,12 +6,12 @@
 // R = L (frame path, method/model.py:318-327) or R = P = 528 clip proposals.
 //
 // Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0  : TMA producer for the corpus (B) ring — BLOCK_N rows x 64 features per stage
-//   warp 1  : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
-//   warp 2  : TMA producer for the query tile (A: 128 queries x D, resident for a whole work
+//   warp 8  : TMA producer for the corpus (B) ring — BLOCK_N rows x 64 features per K block
+//   warp 9  : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warp 10 : TMA producer for the query tile (A: 128 queries x D, resident for a whole work
 //             item) + TMEM allocation
-//   warp 3  : spare
-//   warps 4-11: epilogue — two warps per TMEM lane quarter, each owning half of the tile's columns
+//   warp 11 : spare
+//   warps 0-7: epilogue — two warps per TMEM lane quarter, each owning half of the tile's columns
 //             (tcgen05.ld 32x32b.x32/.x16), running top-2 per query row across the R / BLOCK_N tiles
 //             of one video; the column position rides in the 4 low mantissa bits of the score
 //             (LOP3 + 3 FMNMX per element), the 16-column chunk id is tracked once per chunk.
@@ -37,6 +37,9 @@ constexpr int kMaxKBlocks = 8;    // D <= 512
 constexpr int kMaxStages = 12;
 constexpr int kNumThreads = 384;
 constexpr int kNumEpiThreads = 256;
+// Warp roles.  The issue scheduler favours higher warp ids within an SM sub-partition, so the three
+// latency-critical single-lane roles sit above the eight ALU-heavy epilogue warps (0..7).
+constexpr int kWarpB = 8, kWarpMma = 9, kWarpA = 10;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -157,6 +160,17 @@ __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, 
   if (t.best != before) t.chunk = cid;
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- cluster / CTA-pair helpers (cta_group::2) --------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -174,7 +188,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // No memory is handed over through this barrier (TMEM reads are ordered by tcgen05.fence), so the
+  // cheap form is enough; ".release.cluster" costs a MEMBAR.ALL.GPU + ERRBAR per arrive.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
@@ -218,12 +234,14 @@ struct GemmParams {
   int M, Mpad, Nv, R, D;
   int block_n;        // columns per MMA tile; R % block_n == 0
   int stages;         // B ring depth
+  int kb_per_stage;   // K blocks (64 features) per ring stage / barrier handshake
   int video_chunk;    // videos per work item
   const uint8_t* mask;
   float* out_max;
   int32_t* out_arg;
   float* out_gap;     // optional: best - runner-up (bf16-level ambiguity of the argmax)
-  int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0
+  int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0,
+                      // 4 = MMA does not wait for the corpus ring, 8 = no corpus TMA at all (timing experiments)
   int64_t ld_out;
 };
 
@@ -250,7 +268,9 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int num_kb = p.D / kBlockK;
   const uint32_t a_kb_bytes = kBlockM * kBlockK * 2;        // 16 KB per K block
   const int b_rows = p.block_n / kCta;                      // corpus rows this CTA stages per K block
-  const uint32_t b_stage_bytes = b_rows * kBlockK * 2;      // b_rows x 128 B
+  const uint32_t b_kb_bytes = b_rows * kBlockK * 2;         // b_rows x 128 B per K block
+  const int kbs = p.kb_per_stage;
+  const uint32_t b_stage_bytes = b_kb_bytes * kbs;
   const uint32_t cta_rank = (kCta == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   uint8_t* smem_a = smem;
@@ -273,8 +293,8 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 8 * kCta); }
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_x); }
-  if (warp == 2) {
+  if (warp == kWarpB && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_x); }
+  if (warp == kWarpA) {
     if (kCta == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kTmemCols));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -288,7 +308,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp == 0) {
+  if (warp == kWarpB) {
     // ===== corpus (B) producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -299,16 +319,20 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int v = v0; v < v1; ++v) {
           for (int t = 0; t < tiles_per_video; ++t) {
             const int row = (p.debug_flags & 2) ? 0 : v * p.R + t * p.block_n;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; kb += kbs) {
+              if (p.debug_flags & 8) continue;
               mbar_wait(&ctl->empty[stage], phase ^ 1);
+              uint8_t* dst = smem_b + (size_t)stage * b_stage_bytes;
               if (kCta == 1) {
                 mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
-                tma_load_2d(&map_x, &ctl->full[stage], smem_b + (size_t)stage * b_stage_bytes, kb * kBlockK, row);
+                for (int j = 0; j < kbs; ++j)
+                  tma_load_2d(&map_x, &ctl->full[stage], dst + (size_t)j * b_kb_bytes, (kb + j) * kBlockK, row);
               } else {
                 // both halves report to the leader's barrier
                 if (leader) mbar_expect_tx(&ctl->full[stage], 2 * b_stage_bytes);
-                tma_load_2d_pair(&map_x, mapa_u32(smem_u32(&ctl->full[stage]), 0), smem_b + (size_t)stage * b_stage_bytes,
-                                 kb * kBlockK, row + (int)cta_rank * b_rows);
+                const uint32_t bar = mapa_u32(smem_u32(&ctl->full[stage]), 0);
+                for (int j = 0; j < kbs; ++j)
+                  tma_load_2d_pair(&map_x, bar, dst + (size_t)j * b_kb_bytes, (kb + j) * kBlockK, row + (int)cta_rank * b_rows);
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -316,7 +340,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kWarpA) {
     // ===== query tile (A) producer =====
     if (lane == 0) {
       uint32_t iphase = 0;
@@ -336,13 +360,28 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         iphase ^= 1;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer =====
-    if (lane == 0 && leader) {
+    if (leader) {
+      // The whole warp walks the schedule (converged); one elected lane issues the tcgen05 instructions.
+      // The issue path is the critical resource of this kernel (the tensor pipe only queues a few MMAs),
+      // so descriptors are built once and advanced with 32-bit immediates, and the wait for the NEXT ring
+      // stage is taken while half of the current stage's MMAs are still queued.
       const uint32_t idesc = make_idesc(p.block_n, kBlockM * kCta);
+      const bool elected = elect_one();
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a));
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b));
+      const uint32_t a_kb_step = a_kb_bytes >> 4, b_kb_step = b_kb_bytes >> 4, b_stage_step = b_stage_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       uint32_t iphase = 0;
       uint32_t tile_ctr = 0;
+      const int steps_per_tile = num_kb / kbs;
+      long long steps_left = 0;  // ring steps this worker will still consume
+      for (int item = worker; item < num_items; item += num_workers) {
+        const int v0 = (item / num_q_tiles) * p.video_chunk;
+        steps_left += (long long)(min(v0 + p.video_chunk, p.Nv) - v0) * tiles_per_video * steps_per_tile;
+      }
+      bool have_full = false;  // full[stage] already observed (software-pipelined wait)
       for (int item = worker; item < num_items; item += num_workers) {
         const int vchunk = item / num_q_tiles;
         const int v0 = vchunk * p.video_chunk;
@@ -357,29 +396,44 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&ctl->full[stage], phase);
+          uint64_t adesc = adesc0;
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kbs) {
+            if (!have_full) mbar_wait(&ctl->full[stage], phase);
+            have_full = false;
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)kb * a_kb_bytes));
-            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)stage * b_stage_bytes));
+            --steps_left;
+            int nstage = stage + 1; uint32_t nphase = phase;
+            if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+            uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_stage_step);
+            for (int j = 0; j < kbs; ++j) {
+              if (elected) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in 16-byte units
-              if (kCta == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-              else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  // +2 (16-byte units) = 32 B = 16 bf16 inside the 128 B swizzle row
+                  if (kCta == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb0 | j | k) ? 1u : 0u);
+                  else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb0 | j | k) ? 1u : 0u);
+                }
+              }
+              adesc += a_kb_step;
+              bdesc += b_kb_step;
+              // absorb the wait for the NEXT stage behind the MMAs just queued
+              if (j == 0 && steps_left > 0 && !(p.debug_flags & 16)) {
+                mbar_wait(&ctl->full[nstage], nphase);
+                have_full = true;
+              }
             }
-            if (kCta == 1) umma_commit(&ctl->empty[stage]); else umma_commit_pair(&ctl->empty[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (elected) { if (kCta == 1) umma_commit(&ctl->empty[stage]); else umma_commit_pair(&ctl->empty[stage]); }
+            stage = nstage; phase = nphase;
           }
-          if (kCta == 1) umma_commit(&ctl->tmem_full[as]); else umma_commit_pair(&ctl->tmem_full[as]);
+          if (elected) { if (kCta == 1) umma_commit(&ctl->tmem_full[as]); else umma_commit_pair(&ctl->tmem_full[as]); }
         }
-        if (kCta == 1) umma_commit(&ctl->a_empty); else umma_commit_pair(&ctl->a_empty);
+        if (elected) { if (kCta == 1) umma_commit(&ctl->a_empty); else umma_commit_pair(&ctl->a_empty); }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===== epilogue =====
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;             // column half of every tile
+    const int half = warp >> 2;                   // column half of every tile
     const int row_in_tile = quarter * 32 + lane;
     const int chunks = p.block_n >> 4;
     const int c_lo = half == 0 ? 0 : ((chunks + 1) >> 1);            // first 16-col chunk of this half
@@ -403,19 +457,22 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)p.block_n;
           const int cid0 = t * chunks;  // chunk id (within the video) of this tile's first chunk
-          int c = (p.debug_flags & 1) ? c_hi : c_lo;
-          for (; c + 2 <= c_hi; c += 2) {
-            uint32_t r[32];
-            tmem_ld32_issue(taddr + (uint32_t)(c << 4), r);
+          // All TMEM loads of this warp's column half are issued back to back and waited for ONCE:
+          // tcgen05.ld latency is long while the tensor pipe is busy, so it is paid per tile, not per chunk.
+          uint32_t r[96];
+          if (!(p.debug_flags & 1)) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int c = c_lo + 2 * i;
+              if (c + 1 < c_hi) tmem_ld32_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+              else if (c < c_hi) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+            }
             tmem_ld_wait();
-            top2_chunk<kHasMask>(t2, r, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
-            top2_chunk<kHasMask>(t2, r + 16, cid0 + c + 1, kHasMask ? mvid + ((cid0 + c + 1) << 4) : nullptr);
-          }
-          if (c < c_hi) {
-            uint32_t r[16];
-            tmem_ld16_issue(taddr + (uint32_t)(c << 4), r);
-            tmem_ld_wait();
-            top2_chunk<kHasMask>(t2, r, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const int c = c_lo + i;
+              if (c < c_hi) top2_chunk<kHasMask>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -458,7 +515,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   tc_fence_before();
   if (kCta == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpA) {
     tc_fence_after();
     if (kCta == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
@@ -497,9 +554,9 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS ? DKD_OK : DKD_ERR_DRIVER;
 }
 
-// Largest multiple of 16 that divides R and is <= 256.
+// Largest multiple of 16 that divides R and is <= 192 (each epilogue warp holds <= 96 columns in registers).
 static int pick_block_n(int R) {
-  for (int n = 256; n >= 16; n -= 16)
+  for (int n = 192; n >= 16; n -= 16)
     if (R % n == 0) return n;
   return 0;
 }
@@ -553,7 +610,14 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
 
   const int num_kb = D / kBlockK;
   const size_t a_bytes = (size_t)num_kb * kBlockM * kBlockK * 2;
-  const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2;
+  // K blocks per ring stage.  Every stage costs one full/empty handshake on the single issuing thread,
+  // which is the scarce resource: CTA pairs (half-size stages) take 3 K blocks per stage when D allows,
+  // measured 1.38 PF vs 1.05 PF with 1 (profiles/r1_gemm_variants.md).  DKD_GEMM_KBS overrides.
+  int kbs = 1;
+  if (cta == 2) kbs = (num_kb % 3 == 0) ? 3 : ((num_kb % 2 == 0) ? 2 : 1);
+  { const char* e = getenv("DKD_GEMM_KBS"); if (e && atoi(e) > 0) kbs = atoi(e); }
+  if (kbs < 1 || num_kb % kbs != 0) kbs = 1;
+  const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2 * kbs;
   const size_t fixed = a_bytes + sizeof(SmemCtl) + 1024 /* alignment slack */ + 256;
   if ((size_t)max_smem < fixed + 2 * b_stage) return DKD_ERR_SHAPE;
   int stages = (int)(((size_t)max_smem - fixed) / b_stage);
@@ -567,7 +631,7 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
   if (rc) return rc;
 
   GemmParams p{};
-  p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages;
+  p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
   { const char* e = getenv("DKD_GEMM_DEBUG"); p.debug_flags = e ? atoi(e) : 0; }
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1

@@ -1,3 +1,4 @@
+"""Developer probe: A/B the scoring GEMM variants inside ONE process (same box, same clocks)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import __graft_entry__ as g; g.load_package()
@@ -10,12 +11,21 @@ def timeit(fn, iters=10, warm=3):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-Nq, Nv, D, P = 10895, 2179, 384, 528
+Nq, Nv, D = 10895, 2179, 384
 dev="cuda"; torch.manual_seed(0)
-q = torch.randn(Nq, D, device=dev); x = torch.randn(Nv*P, D, device=dev)
-Mpad = ops.round_up(Nq,128)
-_, qb = ops.normalize_rows(q, False, True, rows_pad=Mpad)
-_, xb = ops.normalize_rows(x, False, True)
-om = torch.empty(Nq, Nv, device=dev); oa = torch.empty(Nq, Nv, dtype=torch.int32, device=dev)
-t = timeit(lambda: ops.score_max_bf16(qb, Nq, xb, Nv, P, None, om, oa))
-print(f"DKD_GEMM_DEBUG={os.environ.get('DKD_GEMM_DEBUG','0')}: {t:.3f} ms  {2.0*Nq*Nv*P*D/t/1e9:.1f} TFLOP/s")
+configs = sys.argv[1:] or ["cta=2,kbs=1", "cta=1,kbs=1"]
+for R in (528, 128):
+    q = torch.randn(Nq, D, device=dev); x = torch.randn(Nv*R, D, device=dev)
+    Mpad = ops.round_up(Nq,256)
+    _, qb = ops.normalize_rows(q, False, True, rows_pad=Mpad)
+    _, xb = ops.normalize_rows(x, False, True)
+    om = torch.empty(Nq, Nv, device=dev); oa = torch.empty(Nq, Nv, dtype=torch.int32, device=dev); og = torch.empty(Nq, Nv, device=dev)
+    for rep in range(2):
+        for cfg in configs:
+            kv = dict(x.split("=") for x in cfg.split(","))
+            os.environ["DKD_GEMM_CTA"] = kv.get("cta", "2"); os.environ["DKD_GEMM_KBS"] = kv.get("kbs", "1"); os.environ["DKD_GEMM_DEBUG"] = kv.get("dbg", "0")
+            try:
+                t = timeit(lambda: ops.score_max_bf16(qb, Nq, xb, Nv, R, None, om, oa))
+                print(f"R={R} {cfg:24s}: {t:.3f} ms  {2.0*Nq*Nv*R*D/t/1e9:.1f} TFLOP/s", flush=True)
+            except Exception as e:
+                print(f"R={R} {cfg}: {e}")

@@ -192,6 +192,89 @@ dots_kernel(const DotsParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Exact fp32 clip-scale scores, one THREAD per (query, video) pair.
+// Block = (video n, lane y of gridDim.y), 128 threads = 128 query rows of that video's list per tile.
+// The video's T x D clip tile stays in shared memory for the whole block; every lane reads the SAME
+// clip element (LDS.128 broadcast: one wavefront per instruction) and streams its own query row through
+// L1 (16 B per step), so the inner loop is 128 FFMA per 32 LDS + 1 LDG: FMA bound, not LDS bound.
+// Then the T per-clip dots are turned into the T(T+1)/2 window cosines with running sums:
+// max / first argmax over proposals.  Used dense (exact path) and through a CSR (ambiguous pairs of the
+// bf16 GEMM, top-K candidate rescoring).
+struct ClipExactParams {
+  const float* q; int M;
+  const float* clips; const float* scale;
+  int Nv, T, D;
+  float* out_max; int32_t* out_arg; int64_t ld_out;
+  const int32_t* vid_ptr; const int32_t* q_list;
+};
+
+__global__ void __launch_bounds__(128)
+clip_exact_kernel(const ClipExactParams p) {
+  extern __shared__ __align__(16) float smem_ce[];
+  const int ldc = p.D + 4;
+  float* sC = smem_ce;                       // 32 x (D + 4)
+  float* sScale = sC + 32 * ldc;             // 528
+  float* sD = sScale + 528;                  // 32 x 128 (column = thread)
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  int e0 = 0, count = p.M;
+  if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_ptr[n + 1] - e0; }
+  if ((int)blockIdx.y * 128 >= count) return;
+  const int T = p.T, P = T * (T + 1) / 2, D = p.D;
+  const float* cbase = p.clips + (int64_t)n * T * D;
+  for (int i = tid; i < 32 * (D >> 2); i += 128) {
+    const int r = i / (D >> 2), c4 = i % (D >> 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < T) v = *reinterpret_cast<const float4*>(&cbase[(int64_t)r * D + c4 * 4]);
+    *reinterpret_cast<float4*>(&sC[r * ldc + c4 * 4]) = v;
+  }
+  for (int i = tid; i < P; i += 128) sScale[i] = p.scale[(int64_t)n * P + i];
+  __syncthreads();
+
+  for (int tile = blockIdx.y; tile * 128 < count; tile += gridDim.y) {
+    const int r = tile * 128 + tid;
+    const bool live = r < count;
+    const int64_t qrow = live ? (p.q_list ? (int64_t)p.q_list[e0 + r] : (int64_t)r) : 0;
+    const float4* qp = reinterpret_cast<const float4*>(p.q + qrow * D);
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    float4 a = __ldg(qp);
+    for (int k4 = 0; k4 < (D >> 2); ++k4) {
+      const float4 an = (k4 + 1 < (D >> 2)) ? __ldg(qp + k4 + 1) : a;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(&sC[i * ldc + k4 * 4]);
+        acc[i] = fmaf(a.x, b.x, acc[i]);
+        acc[i] = fmaf(a.y, b.y, acc[i]);
+        acc[i] = fmaf(a.z, b.z, acc[i]);
+        acc[i] = fmaf(a.w, b.w, acc[i]);
+      }
+      a = an;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sD[i * 128 + tid] = acc[i];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = 0; s < T; ++s) {
+      float run = 0.f;
+      for (int w = 1; w <= T - s; ++w) {
+        const float d = sD[(s + w - 1) * 128 + tid];
+        run = (w == 1) ? d : __fadd_rn(run, d);
+        const int pi = prop_index(w, s, T);
+        const float v = __fmul_rn(run, sScale[pi]);
+        if (better(v, pi, bv, bi)) { bv = v; bi = pi; }
+      }
+    }
+    if (live) {
+      const int64_t o = p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n;
+      p.out_max[o] = bv;
+      if (p.out_arg) p.out_arg[o] = bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Frame-scale score + branch fusion.  8 lanes per (query, video) pair; block = 256 threads
 // covers 32 queries x 8 videos; grid x = query tiles (fastest) so concurrent blocks share the
 // same 8 videos' table slices in L2.
@@ -342,15 +425,19 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips
                                   void* stream) {
   if (!qn || !clips || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
   if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
-  if (T <= 0 || T > 32 || D <= 0 || D % kKC != 0) return DKD_ERR_SHAPE;
+  if (T <= 0 || T > 32 || D <= 0 || D % 4 != 0 || D > 1024) return DKD_ERR_SHAPE;
   if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
   if (M == 0 || Nv == 0) return DKD_OK;
-  if (M > 65535 * kTM) return DKD_ERR_SHAPE;
-  DotsParams p{};
-  p.q = qn; p.q_video_stride = 0; p.M = M; p.x = clips; p.R = T; p.D = D; p.T = T; p.mask = nullptr;
-  p.scale = prop_scale; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.out_rows = nullptr;
-  p.Nv = Nv; p.vid_ptr = vid_ptr; p.q_list = q_list;
-  return launch_dots<32, EPI_CLIP>(p, Nv, (M + kTM - 1) / kTM, (cudaStream_t)stream);
+  ClipExactParams p{};
+  p.q = qn; p.M = M; p.clips = clips; p.scale = prop_scale; p.Nv = Nv; p.T = T; p.D = D;
+  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.vid_ptr = vid_ptr; p.q_list = q_list;
+  const size_t smem = sizeof(float) * ((size_t)32 * (D + 4) + 528 + 32 * 128);
+  DKD_CUDA_TRY(cudaFuncSetAttribute(clip_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int tiles = (M + 127) / 128;
+  dim3 grid(Nv, tiles < 8 ? tiles : 8);
+  clip_exact_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
 }
 
 extern "C" int dkd_key_clip_dots(const float* key, const float* clips, int32_t Nv, int32_t L, int32_t T,

@@ -46,7 +46,7 @@ def run():
         kk = per[b]["key_clip"].cpu().long()
         assert bool(((kk == br[b]["key_clip"]) | torch.from_numpy(tie)).all()), "exact path: key clip differs beyond ties"
     assert d_ex[~tie].max() <= 5e-6, "exact path: fused scores off"
-    assert tie.mean() < 0.05
+    assert tie.mean() < 0.10
     same = (i_ex.cpu().numpy() == top_ref)
     assert same.mean() > 0.98, f"exact path: ranked ids differ from the oracle ({same.mean():.4f})"
     assert torch.equal(i_bf, i_ex) and torch.equal(s_bf, s_ex), "bf16+rescoring differs from the exact path"

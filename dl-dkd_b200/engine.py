@@ -233,6 +233,10 @@ def merge_shards(local_scores, local_ids, group=None, merge_fn=None):
     M, K = local_scores.shape
     gs = torch.empty((world, M, K), dtype=torch.float32, device=local_scores.device)
     gi = torch.empty((world, M, K), dtype=torch.int32, device=local_scores.device)
-    dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
-    dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
+        dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
+    else:  # gloo (CPU tests): list form
+        dist.all_gather(list(gs.unbind(0)), local_scores.contiguous(), group=group)
+        dist.all_gather(list(gi.unbind(0)), local_ids.contiguous(), group=group)
     return merge_fn(gs, gi)

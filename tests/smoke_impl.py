@@ -47,12 +47,23 @@ def run():
         assert bool(((kk == br[b]["key_clip"]) | torch.from_numpy(tie)).all()), "exact path: key clip differs beyond ties"
     assert d_ex[~tie].max() <= 5e-6, "exact path: fused scores off"
     assert tie.mean() < 0.10
-    same = (i_ex.cpu().numpy() == top_ref)
-    assert same.mean() > 0.98, f"exact path: ranked ids differ from the oracle ({same.mean():.4f})"
+    # Ranking vs the oracle: a tie pair may sit anywhere in the device ranking (its frame-scale term follows
+    # the other, equally valid, key clip), so tie pairs are dropped from both lists; what remains must be the
+    # same sequence up to swaps of scores closer than the fp32 noise floor.
+    got = i_ex.cpu().numpy()
+    n_swapped = 0
+    for m in range(M):
+        a = [v for v in got[m] if not tie[m, v]]
+        b = [v for v in top_ref[m] if not tie[m, v]]
+        assert sorted(a) == sorted(b)
+        for x, y in zip(a, b):
+            if x != y:
+                n_swapped += 1
+                assert abs(fused_ref[m, x] - fused_ref[m, y]) <= 1e-5, "exact path: ranking differs from the oracle"
     assert torch.equal(i_bf, i_ex) and torch.equal(s_bf, s_ex), "bf16+rescoring differs from the exact path"
     fused_bf, _ = engine.score_two_scale_head(pc, pq, "bf16")
     d_bf = np.abs(fused_bf.cpu().numpy() - fused_ref)
     assert np.quantile(d_bf, 0.98) <= 1e-3, "bf16 fused scores beyond 1e-3"
     print("smoke ok: two-scale rank on cuda:0 matches the oracle "
           f"(max |d| exact {d_ex[~tie].max():.2e} outside {int(tie.sum())} fp32 key-clip ties, "
-          f"bf16 p98 {np.quantile(d_bf, 0.98):.2e} max {d_bf.max():.2e})")
+          f"{n_swapped} near-equal swaps in the ranking, bf16 p98 {np.quantile(d_bf, 0.98):.2e} max {d_bf.max():.2e})")

@@ -4,7 +4,8 @@
 //
 // One tiled "dots" kernel: block = 64 query rows x kRows corpus rows of ONE video, K = D streamed
 // in 32-wide chunks through shared memory (padded stride 36 words: conflict-free LDS.128),
-// 256 threads, each thread 2 query rows x kRows/8 corpus rows.  Three epilogues.
+// 256 threads, each thread 2 query rows x kRows/8 corpus rows.  Two epilogues (max/argmax, store).
+// The clip-scale flavour lives in dkd_exact_tc.cu (tensor cores).
 #include "dkd_common.cuh"
 
 namespace dkd {
@@ -13,7 +14,7 @@ constexpr int kTM = 64;      // query rows per block
 constexpr int kKC = 32;      // K chunk
 constexpr int kLd = kKC + 4; // padded smem stride (words); 36 % 32 == 4 -> 8 rows hit 32 banks
 
-enum { EPI_MAX = 0, EPI_CLIP = 1, EPI_STORE = 2 };
+enum { EPI_MAX = 0, EPI_STORE = 2 };
 
 struct DotsParams {
   const float* q;          // query rows
@@ -22,7 +23,6 @@ struct DotsParams {
   const float* x;          // (Nv, R, D)
   int R, D, T;
   const uint8_t* mask;     // (Nv, R) or null
-  const float* scale;      // (Nv, P) EPI_CLIP
   float* out_max;
   int32_t* out_arg;
   int64_t ld_out;
@@ -38,8 +38,6 @@ dots_kernel(const DotsParams p) {
   constexpr int kJ = kRows / 8;
   __shared__ __align__(16) float sQ[kTM * kLd];
   __shared__ __align__(16) float sX[kRows * kLd];
-  __shared__ float sScale[(kEpi == EPI_CLIP) ? 528 : 1];
-  __shared__ float sDots[(kEpi == EPI_CLIP) ? kTM * 33 : 1];
 
   const int n = blockIdx.x;
   const int tile = blockIdx.y;
@@ -123,7 +121,7 @@ dots_kernel(const DotsParams p) {
         if (row < p.T) p.out_rows[((int64_t)n * p.M + lr) * p.T + row] = acc[a][j];
       }
     }
-  } else if constexpr (kEpi == EPI_MAX) {
+  } else {  // EPI_MAX
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int lr = r0 + tm + 32 * a;
@@ -154,122 +152,6 @@ dots_kernel(const DotsParams p) {
         p.out_max[o] = bv;
         if (p.out_arg) p.out_arg[o] = bi;
       }
-    }
-  } else {  // EPI_CLIP: window sums of per-clip dots x prop_scale, max / first argmax over proposals
-    const int T = p.T, P = T * (T + 1) / 2;
-    for (int i = tid; i < P; i += 256) sScale[i] = p.scale[(int64_t)n * P + i];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) sDots[(tm + 32 * a) * 33 + ti + 8 * j] = acc[a][j];
-    __syncthreads();
-    const int m = tid >> 2, sub = tid & 3;  // 4 threads per query row, starts s = sub, sub+4, ...
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int s = sub; s < T; s += 4) {
-      float run = 0.f;
-      for (int w = 1; w <= T - s; ++w) {
-        const float d = sDots[m * 33 + s + w - 1];
-        run = (w == 1) ? d : __fadd_rn(run, d);
-        const int pi = prop_index(w, s, T);
-        const float v = __fmul_rn(run, sScale[pi]);
-        if (better(v, pi, bv, bi)) { bv = v; bi = pi; }
-      }
-    }
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    const int lr = r0 + m;
-    if (lr < count && sub == 0) {
-      const int64_t o = p.vid_ptr ? (int64_t)(e0 + lr) : (int64_t)lr * p.ld_out + n;
-      p.out_max[o] = bv;
-      if (p.out_arg) p.out_arg[o] = bi;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Exact fp32 clip-scale scores, one THREAD per (query, video) pair.
-// Block = (video n, lane y of gridDim.y), 128 threads = 128 query rows of that video's list per tile.
-// The video's T x D clip tile stays in shared memory for the whole block; every lane reads the SAME
-// clip element (LDS.128 broadcast: one wavefront per instruction) and streams its own query row through
-// L1 (16 B per step), so the inner loop is 128 FFMA per 32 LDS + 1 LDG: FMA bound, not LDS bound.
-// Then the T per-clip dots are turned into the T(T+1)/2 window cosines with running sums:
-// max / first argmax over proposals.  Used dense (exact path) and through a CSR (ambiguous pairs of the
-// bf16 GEMM, top-K candidate rescoring).
-struct ClipExactParams {
-  const float* q; int M;
-  const float* clips; const float* scale;
-  int Nv, T, D;
-  float* out_max; int32_t* out_arg; int64_t ld_out;
-  const int32_t* vid_ptr; const int32_t* q_list;
-};
-
-__global__ void __launch_bounds__(128)
-clip_exact_kernel(const ClipExactParams p) {
-  extern __shared__ __align__(16) float smem_ce[];
-  const int ldc = p.D + 4;
-  float* sC = smem_ce;                       // 32 x (D + 4)
-  float* sScale = sC + 32 * ldc;             // 528
-  float* sD = sScale + 528;                  // 32 x 128 (column = thread)
-  const int n = blockIdx.x;
-  const int tid = threadIdx.x;
-  int e0 = 0, count = p.M;
-  if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_ptr[n + 1] - e0; }
-  if ((int)blockIdx.y * 128 >= count) return;
-  const int T = p.T, P = T * (T + 1) / 2, D = p.D;
-  const float* cbase = p.clips + (int64_t)n * T * D;
-  for (int i = tid; i < 32 * (D >> 2); i += 128) {
-    const int r = i / (D >> 2), c4 = i % (D >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) v = *reinterpret_cast<const float4*>(&cbase[(int64_t)r * D + c4 * 4]);
-    *reinterpret_cast<float4*>(&sC[r * ldc + c4 * 4]) = v;
-  }
-  for (int i = tid; i < P; i += 128) sScale[i] = p.scale[(int64_t)n * P + i];
-  __syncthreads();
-
-  for (int tile = blockIdx.y; tile * 128 < count; tile += gridDim.y) {
-    const int r = tile * 128 + tid;
-    const bool live = r < count;
-    const int64_t qrow = live ? (p.q_list ? (int64_t)p.q_list[e0 + r] : (int64_t)r) : 0;
-    const float4* qp = reinterpret_cast<const float4*>(p.q + qrow * D);
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    float4 a = __ldg(qp);
-    for (int k4 = 0; k4 < (D >> 2); ++k4) {
-      const float4 an = (k4 + 1 < (D >> 2)) ? __ldg(qp + k4 + 1) : a;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float4 b = *reinterpret_cast<const float4*>(&sC[i * ldc + k4 * 4]);
-        acc[i] = fmaf(a.x, b.x, acc[i]);
-        acc[i] = fmaf(a.y, b.y, acc[i]);
-        acc[i] = fmaf(a.z, b.z, acc[i]);
-        acc[i] = fmaf(a.w, b.w, acc[i]);
-      }
-      a = an;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) sD[i * 128 + tid] = acc[i];
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int s = 0; s < T; ++s) {
-      float run = 0.f;
-      for (int w = 1; w <= T - s; ++w) {
-        const float d = sD[(s + w - 1) * 128 + tid];
-        run = (w == 1) ? d : __fadd_rn(run, d);
-        const int pi = prop_index(w, s, T);
-        const float v = __fmul_rn(run, sScale[pi]);
-        if (better(v, pi, bv, bi)) { bv = v; bi = pi; }
-      }
-    }
-    if (live) {
-      const int64_t o = p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n;
-      p.out_max[o] = bv;
-      if (p.out_arg) p.out_arg[o] = bi;
     }
   }
 }
@@ -411,33 +293,12 @@ extern "C" int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, in
   if (M > 65535 * kTM) return DKD_ERR_SHAPE;
   DotsParams p{};
   p.q = qn; p.q_video_stride = 0; p.M = M; p.x = xn; p.R = R; p.D = D; p.T = 0; p.mask = mask;
-  p.scale = nullptr; p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.out_rows = out_rows;
+  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.out_rows = out_rows;
   p.Nv = Nv; p.vid_ptr = vid_ptr; p.q_list = q_list;
   const int tiles = (M + kTM - 1) / kTM;
   if (R <= 32) return launch_dots<32, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
   if (R <= 64) return launch_dots<64, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
   return launch_dots<128, EPI_MAX>(p, Nv, tiles, (cudaStream_t)stream);
-}
-
-extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const float* prop_scale,
-                                  int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
-                                  int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
-                                  void* stream) {
-  if (!qn || !clips || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
-  if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
-  if (T <= 0 || T > 32 || D <= 0 || D % 4 != 0 || D > 1024) return DKD_ERR_SHAPE;
-  if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
-  if (M == 0 || Nv == 0) return DKD_OK;
-  ClipExactParams p{};
-  p.q = qn; p.M = M; p.clips = clips; p.scale = prop_scale; p.Nv = Nv; p.T = T; p.D = D;
-  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out; p.vid_ptr = vid_ptr; p.q_list = q_list;
-  const size_t smem = sizeof(float) * ((size_t)32 * (D + 4) + 528 + 32 * 128);
-  DKD_CUDA_TRY(cudaFuncSetAttribute(clip_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int tiles = (M + 127) / 128;
-  dim3 grid(Nv, tiles < 8 ? tiles : 8);
-  clip_exact_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
-  DKD_LAUNCH_CHECK();
-  return DKD_OK;
 }
 
 extern "C" int dkd_key_clip_dots(const float* key, const float* clips, int32_t Nv, int32_t L, int32_t T,

@@ -22,10 +22,11 @@ PROTOTYPES = {
     "dkd_downsample_clips": [_P, _P, _I, _I, _I, _I, _P, _P],
     "dkd_build_proposals": [_P, _I, _I, _I, _P, _P, _P, _P],
     "dkd_score_max_f32": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P],
-    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P],
+    "dkd_clip_planes_bytes": [_I, _I],
+    "dkd_pack_clips_tf32": [_P, _I, _I, _I, _P, _P],
+    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P],
     "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P],
     "dkd_select_pairs_csr": [_P, _I, _I, _L, _F, _L, _P, _P, _P, _P, _P],
-    "dkd_scatter_pairs": [_P, _P, _P, _P, _I, _L, _P, _P, _P],
     "dkd_key_clip_dots": [_P, _P, _I, _I, _I, _I, _P, _P],
     "dkd_frame_attn_table": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "dkd_frame_fuse": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _L, _F, _F, _F, _I, _P, _P, _P],
@@ -38,7 +39,7 @@ PROTOTYPES = {
     "dkd_scatter_fuse": [_P, _P, _F, _F, _P, _P, _I, _L, _P, _P],
     "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
 }
-_RESTYPES = {"dkd_error_string": c_char_p}
+_RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64}
 
 _lib = None
 

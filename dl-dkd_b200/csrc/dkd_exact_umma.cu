@@ -1,0 +1,472 @@
+// Exact (fp32-grade) clip-scale scores on the tcgen05 tensor cores.
+//
+//   d[i]        = qn[m] . clips[n, i]                       i = 0..T-1      tcgen05.mma kind::tf32, 3 products
+//   S[p(w, s)]  = (d[s] + d[s+1] + ... + d[s+w-1]) * prop_scale[n, p]       fp32 running sums in registers
+//   out_max     = max_p S,   out_arg = first argmax_p       (torch.max tie rule)
+//
+// fp32 accuracy from tf32 tensor cores by operand splitting: x = hi + lo with hi = tf32(x), lo = tf32(x - hi)
+// (done by the staging warps on the way into shared memory), d = lo.hi + hi.lo + hi.hi accumulated in one fp32 TMEM
+// accumulator — relative error per product ~2^-21, inside the summation-order noise of an fp32 einsum.
+// This is the fp32 flavour of get_clip_scale_scores: (a) the exact drop-in path (dense),
+// (b) re-resolution of the pairs whose bf16 argmax is ambiguous, (c) rescoring of the top-K candidates;
+// (b) and (c) address the pairs through a CSR by video (vid_ptr / q_list).
+//
+// One persistent CTA per SM walks videos; a tile = 128 list entries of one video (UMMA M = 128, N = 32 clips).
+// The A operand (query rows) lives in TENSOR MEMORY: with N = 32 an MMA that re-reads a 128-row A tile from
+// shared memory is shared-memory-bandwidth bound (5 KB per 16-cycle MMA), from TMEM it runs at the MMA floor.
+//   warps 0-3   scan: tcgen05.ld of the lane's 32 dots, 528 running window sums x scale, max/first argmax
+//               (thread = tile row; 8 independent running maxima per thread)
+//   warps 4-11  stagers (two per TMEM lane quarter, alternating K blocks): cp.async gather of the fp32 query rows
+//               (32 features per K block) into a per-warp ring, split into tf32 hi / lo, tcgen05.st.16x256b into
+//               the A ring (64 columns per stage)
+//   warp 12     tcgen05.mma issuer (one elected lane, A from TMEM, B from smem) + TMEM allocation
+//               (512 columns: 2 x 32 accumulator + 7 x 64 A ring)
+//   warp 13     B loader: one cp.async.bulk per video of its pre-packed clip planes (dkd_pack_clips_tf32: the
+//               shared-memory image of the B operand — tf32 hi / lo planes, K-major SWIZZLE_128B)
+#include "dkd_umma.cuh"
+
+namespace dkd {
+
+constexpr int kXRows = 128;                 // list entries per tile
+constexpr int kXKB = 32;                    // fp32 features per K block (one 128-byte swizzle row)
+constexpr int kXScanWarps = 4;              // one per TMEM lane quarter: thread = tile row
+constexpr int kXStageWarps = 8;             // two per TMEM lane quarter, alternating K blocks
+constexpr int kXStagers = 4 * 32;            // stager threads that fill one A stage (one warp per quarter)
+constexpr int kXMmaWarp = kXScanWarps + kXStageWarps;
+constexpr int kXLoadWarp = kXMmaWarp + 1;   // B-operand loader (cp.async.bulk of the pre-packed clip planes)
+constexpr int kXThreads = (kXLoadWarp + 1) * 32;
+constexpr int kXStages = 7;               // A ring stages in TMEM: 64 + 7 * 64 = 512 columns
+constexpr uint32_t kXBPlane = 32 * 128;      // 4 KB : 32 clips x 128 B
+constexpr int kXTmemCols = 512;
+constexpr uint32_t kXACol0 = 64;            // first A-ring column
+constexpr uint32_t kXRowPitch = 128;        // staged fp32 row of one K block; 16-byte chunk c of row r sits at
+                                            // chunk c ^ ((r & 1) << 2): conflict-free cp.async writes and LDS.128 reads
+constexpr uint32_t kXSlotBytes = 32 * kXRowPitch;
+// per-stager-warp cp.async ring: kRing slots (kRing - 1 of the warp's K blocks in flight), 3 normally, 2 when D > 448
+
+struct ExactParams {
+  const float* q; int M;
+  const float* planes; const float* scale;
+  int Nv, T, D;
+  int b_bufs;
+  float* out_max; int32_t* out_arg; int64_t ld_out;
+  const int32_t* vid_ptr; const int32_t* q_list; const int32_t* out_slot;
+};
+
+struct __align__(8) ExactCtl {
+  uint64_t a_full[kXStages], a_empty[kXStages];
+  uint64_t b_full[2], b_empty[2];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// hi = tf32(x) rounded to nearest; lo = x - hi exactly (<= 13 significant bits).  The tensor core reads only the
+// tf32 part of lo (drops its low 13 bits: <= 2^-21 |x|, sign-symmetric because hi is rounded to nearest).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// 16 lanes x 32 columns: reg 4j+e -> (lane g = tid/4, col 8j + 2(tid%4) + e), reg 4j+2+e -> lane g + 8
+// (layout verified on hardware: tools/micro/tmem_layout.cu)
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem], tf32 x tf32 -> fp32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// kind::tf32: D = f32, A = B = tf32 (format 2), both K-major
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int n, int m) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B plane (8-row groups of 1024 B)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void video_range(const ExactParams& p, int n, int& e0, int& count) {
+  if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_ptr[n + 1] - e0; }
+  else { e0 = 0; count = p.M; }
+}
+
+template <bool kT32, int kXRing>
+__global__ void __launch_bounds__(kXThreads, 1)
+clip_exact_umma_kernel(const ExactParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw_x[];
+  __shared__ float s_scale[2][528];   // prop_scale row of the current video (scan warps, double buffered)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_x) + 1023) & ~(uintptr_t)1023);
+  const int num_kb = p.D / kXKB;
+  const uint32_t b_buf_bytes = (uint32_t)num_kb * 2u * kXBPlane;
+  uint8_t* sB = smem;                                           // [buf][kb][plane] x 4 KB
+  uint8_t* sS = sB + (size_t)p.b_bufs * b_buf_bytes;            // [stager warp][slot][32 rows] x 192 B
+  ExactCtl* ctl = reinterpret_cast<ExactCtl*>(sS + (size_t)kXStageWarps * kXRing * kXSlotBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_bufs = (uint32_t)p.b_bufs;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&ctl->a_full[i], kXStagers); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->b_full[i], 1);
+      mbar_init(&ctl->b_empty[i], 1);
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], kXScanWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kXMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(kXTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp >= kXScanWarps && warp < kXMmaWarp) {
+    // ===================== stagers =====================
+    // Query rows are gathered as fp32 (coalesced 128-byte row segments) by cp.async into a private per-warp
+    // ring (kXRing - 1 K blocks in flight per warp: the gather is latency bound, the bytes in flight set its
+    // bandwidth), read back as tcgen05.st.16x256b fragments, split into tf32 hi / lo and stored to the TMEM A
+    // ring, whose 7 stages decouple the stagers from the MMA.
+    const int quarter = warp & 3, par = (warp - kXScanWarps) >> 2;   // this warp stages items j = par (mod 2)
+    const int g = lane >> 2, t = lane & 3;
+    const int cl_row = lane >> 3, cl_chunk = lane & 7;          // cp.async: 4 rows x 8 chunks per instruction
+    const uint32_t a_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + kXACol0;
+    const int sw = warp - kXScanWarps;                          // 0..7
+    const uint32_t ring0 = smem_u32(sS) + (uint32_t)sw * kXRing * kXSlotBytes;
+    const uint8_t* ring_ptr = sS + (size_t)sw * kXRing * kXSlotBytes;
+    uint32_t it_base = 0;                                       // A ring counter of item 0 of the current video
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int e0, count;
+      video_range(p, n, e0, count);
+      if (count <= 0) continue;
+      const int nitems = ((count + kXRows - 1) / kXRows) * num_kb;
+      // item j = (tile j / num_kb, K block j % num_kb) of this video
+      int t_cached = -1;
+      const float* src_cached[8];
+      uint32_t live_mask = 0;
+      int iss_tile = 0, iss_kb = par;                           // (tile, K block) of this warp's next item to issue
+      while (iss_kb >= num_kb) { iss_kb -= num_kb; ++iss_tile; }
+      auto issue = [&](int slot) {
+        const int tile = iss_tile, kb = iss_kb;
+        iss_kb += 2;
+        while (iss_kb >= num_kb) { iss_kb -= num_kb; ++iss_tile; }
+        if (tile != t_cached) {
+          t_cached = tile;
+          live_mask = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = tile * kXRows + quarter * 32 + 4 * i + cl_row;
+            const bool live = r < count;
+            const int64_t qrow = live ? (p.q_list ? (int64_t)p.q_list[e0 + r] : (int64_t)r) : 0;
+            src_cached[i] = p.q + qrow * p.D + 4 * cl_chunk;
+            live_mask |= (live ? 1u : 0u) << i;
+          }
+        }
+        // rows 4i + cl_row: (row & 1) == (cl_row & 1)
+        const uint32_t dst = ring0 + (uint32_t)slot * kXSlotBytes + (uint32_t)cl_row * kXRowPitch +
+                             (uint32_t)((cl_chunk ^ ((cl_row & 1) << 2)) << 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          cp_async16(dst + (uint32_t)(4 * i) * kXRowPitch, src_cached[i] + kb * kXKB, ((live_mask >> i) & 1u) ? 16u : 0u);
+      };
+      auto store = [&](int j, int slot_i) {
+        // fragments of item j: rows 16h + g + 8u ((row & 1) == (g & 1)), features 16c + 4t .. +3 (chunk 4c + t)
+        const uint8_t* slot = ring_ptr + (size_t)slot_i * kXSlotBytes;
+        float4 v[8];
+#pragma unroll
+        for (int hu = 0; hu < 4; ++hu)
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            v[2 * hu + c] = *reinterpret_cast<const float4*>(
+                slot + (16 * (hu >> 1) + g + 8 * (hu & 1)) * kXRowPitch + (((4 * c + t) ^ ((g & 1) << 2)) << 4));
+        const uint32_t it = it_base + (uint32_t)j;
+        const uint32_t stage = it % (uint32_t)kXStages;
+        const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
+        mbar_wait(&ctl->a_empty[stage], phase ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // TMEM column 8(2c+b) + 2t + e of the K block holds feature 16c + 4t + 2b + e (the clip planes in
+          // shared memory use the same permutation).  lo = x - hi is exact; the MMA drops its low 13 bits.
+          uint32_t rh[16], rl[16];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const float4 x = v[2 * (2 * h + u) + c];
+              split_tf32(x.x, rh[4 * (2 * c) + 2 * u + 0], rl[4 * (2 * c) + 2 * u + 0]);
+              split_tf32(x.y, rh[4 * (2 * c) + 2 * u + 1], rl[4 * (2 * c) + 2 * u + 1]);
+              split_tf32(x.z, rh[4 * (2 * c + 1) + 2 * u + 0], rl[4 * (2 * c + 1) + 2 * u + 0]);
+              split_tf32(x.w, rh[4 * (2 * c + 1) + 2 * u + 1], rl[4 * (2 * c + 1) + 2 * u + 1]);
+            }
+          const uint32_t ta = a_lane + ((uint32_t)(16 * h) << 16) + stage * 64u;
+          tmem_st_16x256b_x4(ta, rh);
+          tmem_st_16x256b_x4(ta + 32u, rl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&ctl->a_full[stage]);
+      };
+      // this warp's items: j = 2m + par.  Prologue: the first kXRing - 1 of them (one commit group per item,
+      // empty groups keep the count uniform)
+      const int nmine = (nitems - par + 1) / 2;
+#pragma unroll
+      for (int m = 0; m < kXRing - 1; ++m) {
+        if (m < nmine) issue(m);
+        cp_async_commit();
+      }
+      for (int m = 0; m < nmine; ++m) {
+        if (m + kXRing - 1 < nmine) issue((m + kXRing - 1) % kXRing);   // the slot item m - 1 was read from
+        cp_async_commit();
+        cp_async_wait<kXRing - 1>();                            // item m has landed
+        __syncwarp();
+        store(2 * m + par, m % kXRing);
+        __syncwarp();                                           // every lane is done with the slot
+      }
+      cp_async_wait<0>();
+      it_base += (uint32_t)nitems;
+    }
+  } else if (warp == kXLoadWarp) {
+    // ===================== B loader =====================
+    if (lane == 0) {
+      uint32_t vi = 0;
+      for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+        int e0, count;
+        video_range(p, n, e0, count);
+        if (count <= 0) continue;
+        const uint32_t bb = vi % b_bufs;
+        mbar_wait(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u);
+        ++vi;
+        mbar_expect_tx(&ctl->b_full[bb], b_buf_bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * b_buf_bytes;
+        for (int kb = 0; kb < num_kb; ++kb)                       // 8 KB per K block: hi plane, lo plane
+          bulk_load(sB + (size_t)bb * b_buf_bytes + (size_t)kb * 2 * kXBPlane, src + (size_t)kb * 2 * kXBPlane,
+                    2 * kXBPlane, &ctl->b_full[bb]);
+      }
+    }
+  } else if (warp == kXMmaWarp) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_tf32(32, kXRows);
+    const bool elected = elect_one();
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(sB));
+    uint32_t it = 0, vi = 0, tc = 0;
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int e0, count;
+      video_range(p, n, e0, count);
+      if (count <= 0) continue;
+      const uint32_t bb = vi % b_bufs;
+      mbar_wait(&ctl->b_full[bb], (vi / b_bufs) & 1u);
+      ++vi;
+      const uint64_t bdesc_v = bdesc0 + (uint64_t)((bb * b_buf_bytes) >> 4);
+      for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 32u;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t stage = it % (uint32_t)kXStages;
+          const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
+          mbar_wait(&ctl->a_full[stage], phase);
+          tc_fence_after();
+          if (elected) {
+            const uint32_t a_hi = tmem_base + kXACol0 + stage * 64u;
+            const uint32_t a_lo = a_hi + 32u;
+            const uint64_t b_hi = bdesc_v + (uint64_t)(((uint32_t)kb * 2u * kXBPlane) >> 4);
+            const uint64_t b_lo = b_hi + (uint64_t)(kXBPlane >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 8 tf32 per MMA: 8 TMEM columns of A, 32 B (+2 x 16 B) of the B swizzle row
+              umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);   // small terms first
+              umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
+            }
+            umma_commit(&ctl->a_empty[stage]);
+          }
+          __syncwarp();
+        }
+        if (elected) umma_commit(&ctl->tmem_full[buf]);
+        __syncwarp();
+      }
+      if (elected) umma_commit(&ctl->b_empty[bb]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== scan =====================
+    // Thread = tile row.  Windows are visited w-major, so inside each of the 8 independent running maxima
+    // (start class s & 7) proposal indices increase and strict > keeps the first maximum; the final merge
+    // compares (value desc, index asc).
+    const int T = p.T, P = T * (T + 1) / 2;
+    const int quarter = warp;
+    const int stid = threadIdx.x;                                   // 0..127 among scan threads
+    uint32_t tc = 0, vi = 0;
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int e0, count;
+      video_range(p, n, e0, count);
+      if (count <= 0) continue;
+      float* sc = s_scale[vi & 1u];
+      // the buffer was last read two videos ago; the barrier below (one per video) orders those reads before
+      // these writes: a warp can be at most one video ahead of the slowest one
+      for (int i = stid; i < P; i += kXScanWarps * 32) sc[i] = __ldg(p.scale + (int64_t)n * P + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(kXScanWarps * 32) : "memory");
+      ++vi;
+      for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(&ctl->tmem_full[buf], (tc >> 1) & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 32u, raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+        float d[32], run[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
+        float bv[8];
+        int bi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
+#pragma unroll
+        for (int w = 1; w <= 32; ++w) {
+#pragma unroll
+          for (int s = 0; s + w <= 32; ++s) {
+            run[s] = (w == 1) ? d[s] : __fadd_rn(run[s], d[s + w - 1]);
+            if (kT32 || s + w <= T) {
+              const int pi = kT32 ? ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s) : ((w - 1) * T - ((w - 1) * (w - 2)) / 2 + s);
+              const float v = __fmul_rn(run[s], sc[pi]);
+              if (v > bv[s & 7]) { bv[s & 7] = v; bi[s & 7] = pi; }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+          if (better(bv[k], bi[k], bv[0], bi[0])) { bv[0] = bv[k]; bi[0] = bi[k]; }
+        const int r = t0 + quarter * 32 + lane;
+        if (r < count) {
+          const int64_t o = p.out_slot ? (int64_t)p.out_slot[e0 + r]
+                                       : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n);
+          p.out_max[o] = bv[0];
+          if (p.out_arg) p.out_arg[o] = bi[0];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kXMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kXTmemCols));
+  }
+}
+
+// Pre-pack the clips of every video into the shared-memory image of the exact kernel's B operand:
+// planes[n][kb][plane][32 rows x 128 B, SWIZZLE_128B], plane 0 = tf32 hi, 1 = tf32 lo, rows >= T zero, features
+// of a K block permuted like the A operand (feature 16c + 4t + 2b + e at position 16c + 8b + 2t + e).
+__global__ void pack_clips_tf32_kernel(const float* __restrict__ clips, int T, int D, float* __restrict__ planes) {
+  const int n = blockIdx.x;
+  const int num_kb = D / kXKB;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(planes) + (size_t)n * num_kb * 2 * kXBPlane;
+  for (int i = threadIdx.x; i < num_kb * 256; i += blockDim.x) {
+    const int kb = i >> 8, r = (i >> 3) & 31, c8 = i & 7;         // float4 c8: features 4 c8 .. 4 c8 + 3
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < T) v = *reinterpret_cast<const float4*>(clips + ((int64_t)n * T + r) * D + kb * kXKB + c8 * 4);
+    uint2 h0, l0, h1, l1;
+    split_tf32(v.x, h0.x, l0.x); split_tf32(v.y, h0.y, l0.y); split_tf32(v.z, h1.x, l1.x); split_tf32(v.w, h1.y, l1.y);
+    const int cc = c8 >> 2, tt = c8 & 3;
+    const int p0 = 16 * cc + 2 * tt;                                // b = 0; b = 1 is 8 positions further
+    uint8_t* row0 = dst + (size_t)(kb * 2) * kXBPlane;
+    uint8_t* d0 = row0 + sw128_off(r, p0 >> 2) + (p0 & 3) * 4;
+    uint8_t* d1 = row0 + sw128_off(r, (p0 + 8) >> 2) + (p0 & 3) * 4;
+    *reinterpret_cast<uint2*>(d0) = h0;
+    *reinterpret_cast<uint2*>(d1) = h1;
+    *reinterpret_cast<uint2*>(d0 + kXBPlane) = l0;
+    *reinterpret_cast<uint2*>(d1 + kXBPlane) = l1;
+  }
+}
+
+}  // namespace dkd
+
+using namespace dkd;
+
+extern "C" int64_t dkd_clip_planes_bytes(int32_t Nv, int32_t D) {
+  if (Nv < 0 || D <= 0 || D % kXKB != 0) return -1;
+  return (int64_t)Nv * (D / kXKB) * 2 * kXBPlane;
+}
+
+extern "C" int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream) {
+  if (!clips || !planes || Nv < 0) return DKD_ERR_ARG;
+  if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(clips) | reinterpret_cast<uintptr_t>(planes)) & 15) return DKD_ERR_ALIGN;
+  if (Nv == 0) return DKD_OK;
+  pack_clips_tf32_kernel<<<Nv, 256, 0, (cudaStream_t)stream>>>(clips, T, D, planes);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
+                                  int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
+                                  int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
+                                  const int32_t* out_slot, void* stream) {
+  if (!qn || !clip_planes || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
+  if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
+  if (out_slot && !vid_ptr) return DKD_ERR_ARG;
+  if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
+  if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(clip_planes) | reinterpret_cast<uintptr_t>(prop_scale)) & 15)
+    return DKD_ERR_ALIGN;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  int dev = 0, sms = 0, max_smem = 0;
+  DKD_CUDA_TRY(cudaGetDevice(&dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int num_kb = D / kXKB;
+  const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
+  const int ring = D > 448 ? 2 : 3;
+  const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 8192 /* static shared */ + (size_t)kXStageWarps * ring * kXSlotBytes;
+  if ((size_t)max_smem < fixed + b_buf) return DKD_ERR_SHAPE;
+  const int b_bufs = ((size_t)max_smem >= fixed + 2 * b_buf) ? 2 : 1;
+  const size_t smem = fixed - 8192 + (size_t)b_bufs * b_buf;
+  ExactParams p{};
+  p.q = qn; p.M = M; p.planes = clip_planes; p.scale = prop_scale;
+  p.Nv = Nv; p.T = T; p.D = D; p.b_bufs = b_bufs;
+  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
+  p.vid_ptr = vid_ptr; p.q_list = q_list; p.out_slot = out_slot;
+  const int grid = Nv < sms ? Nv : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto launch = [&](auto kern) -> int {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kXThreads, smem, st>>>(p);
+    return DKD_OK;
+  };
+  int rc;
+  if (ring == 3) rc = (T == 32) ? launch(clip_exact_umma_kernel<true, 3>) : launch(clip_exact_umma_kernel<false, 3>);
+  else rc = (T == 32) ? launch(clip_exact_umma_kernel<true, 2>) : launch(clip_exact_umma_kernel<false, 2>);
+  if (rc) return rc;
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}

@@ -227,19 +227,6 @@ __global__ void pair_fill_kernel(const float* __restrict__ gap, int M, int Nv, i
     }
   }
 }
-// out_clip[slot[e]] = cs[e]; out_key[slot[e]] = ck[e]
-__global__ void pair_scatter_kernel(const float* __restrict__ cs, const int32_t* __restrict__ ck,
-                                    const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
-                                    int64_t cap, float* __restrict__ out_clip, int32_t* __restrict__ out_key) {
-  int64_t total = *total_ptr;
-  if (total > cap) total = cap;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int sl = slot[i];
-    out_clip[sl] = cs[i];
-    out_key[sl] = ck[i];
-  }
-}
-
 // out[slot[e]] = fl(wa * a[e]) + fl(wb * b[e])  (b may be null: out[slot[e]] = a[e])
 __global__ void scatter_fuse_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
                                     const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
@@ -357,15 +344,6 @@ extern "C" int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int
   cand_scan_kernel<<<1, 1024, 0, st>>>(counts, Nv, vid_ptr);
   DKD_LAUNCH_CHECK();
   pair_fill_kernel<<<blocks, 256, 0, st>>>(gap, M, Nv, ld, tau, counts, vid_ptr, q_list, slot, cap);
-  DKD_LAUNCH_CHECK();
-  return DKD_OK;
-}
-
-extern "C" int dkd_scatter_pairs(const float* cs, const int32_t* ck, const int32_t* slot, const int32_t* vid_ptr,
-                                 int32_t Nv, int64_t cap, float* out_clip, int32_t* out_key, void* stream) {
-  if (!cs || !ck || !slot || !vid_ptr || !out_clip || !out_key || Nv <= 0 || cap < 0) return DKD_ERR_ARG;
-  if (cap == 0) return DKD_OK;
-  pair_scatter_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(cs, ck, slot, vid_ptr + Nv, cap, out_clip, out_key);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -15,7 +15,7 @@ Two precisions
 HBM layout per branch (Nv videos, L frames, D features, T clips, P = T(T+1)/2 proposals):
   frames_n   (Nv, L, D) fp32   L2-normalised frames          frame head, exact
   frames_b   (Nv*L, D)  bf16   same, GEMM B operand          frame head, bf16
-  clips      (Nv, T, D) fp32   downsampled clips             two-scale, exact + rescoring
+  clips      (Nv, T, D) fp32   downsampled clips  two-scale, exact + rescoring
   prop_scale (Nv, P)    fp32   1/(w*||mean||)                two-scale, exact + rescoring
   prop_b     (Nv*P, D)  bf16   L2-normalised proposals       two-scale GEMM B operand
   table_f    (Nv, P, D) fp32   normalised attention outputs  frame-scale, exact + rescoring
@@ -38,6 +38,7 @@ class BranchData:
     frames_n: Optional[torch.Tensor] = None
     frames_b: Optional[torch.Tensor] = None
     clips: Optional[torch.Tensor] = None
+    clip_planes: Optional[torch.Tensor] = None
     prop_scale: Optional[torch.Tensor] = None
     prop_b: Optional[torch.Tensor] = None
     table_f: Optional[torch.Tensor] = None
@@ -97,6 +98,7 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
                 raise ValueError("two_scale head needs the key/value projections (attn_params)")
             kw, kb, vw, vb = attn_params[bi]
             bd.clips = ops.downsample_clips(fr, lengths, T)
+            bd.clip_planes = ops.pack_clips(bd.clips)
             pb, ps, _ = ops.build_proposals(bd.clips, want_bf16="bf16" in precisions, want_scale=True)
             bd.prop_b = None if pb is None else pb.view(-1, D)
             bd.prop_scale = ps
@@ -155,21 +157,20 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
     precision="bf16": the tcgen05 GEMM also reports, per (query, video), the gap between the best and
     the runner-up proposal.  The key clip steers the frame-scale term discontinuously, so pairs whose
     gap is below `tau` (the bf16 noise floor on score differences) get their clip score and key clip
-    recomputed by the exact fp32 kernel before the frame-scale gather; tau=0 disables the pass."""
+    recomputed by the exact kernel before the frame-scale gather; tau=0 disables the pass."""
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
     fused = None
     per = []
     for bi, (bd, qn, qb) in enumerate(zip(pc.branches, pq.qn, pq.qb)):
         if precision == "exact":
-            s_clip, k_clip = ops.clip_score_f32(qn, bd.clips, bd.prop_scale)
+            s_clip, k_clip = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale)
             q, tab = qn, bd.table_f
         else:
             if tau > 0:
                 s_clip, k_clip, gap = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P, want_gap=True)
                 csr = ops.select_pairs_csr(gap, tau)
-                cs, ck = ops.clip_score_f32(qn, bd.clips, bd.prop_scale, csr=csr[:2])
-                ops.scatter_pairs(cs, ck, csr, s_clip, k_clip)
+                ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2], scatter=(csr[2], s_clip, k_clip))
             else:
                 s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
             q, tab = qb, bd.table_b
@@ -209,7 +210,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             ops.scatter_fuse(ex[0], None, 1.0, 0.0, csr, cand_scores)
     else:
         for bi, (bd, qn) in enumerate(zip(pc.branches, pq.qn)):
-            cs, ck = ops.clip_score_f32(qn, bd.clips, bd.prop_scale, csr=csr[:2])
+            cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2])
             wb = wbs[bi] if nb == 2 else 1.0
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
     return ops.sort_candidates(cand_scores, cand, K)

@@ -101,26 +101,51 @@ def score_max_f32(qn, xn, mask=None, want_rows=False, csr=None):
     return om, oa, rows
 
 
-def clip_score_f32(qn, clips, prop_scale, csr=None):
-    """Exact fp32 clip-scale max/argmax over the P proposals via per-clip dots."""
-    _chk(qn, torch.float32, "qn")
+def pack_clips(clips):
+    """(Nv, T, D) clips -> (Nv, D/32, 2, 32, 32) fp32: the pre-packed B operand of the exact clip-scale kernel
+    (tf32 hi / lo planes in the shared-memory layout; once per corpus)."""
     _chk(clips, torch.float32, "clips")
+    Nv, T, D = clips.shape
+    if D % 32:
+        raise _lib.DkdError("pack_clips: D must be a multiple of 32")
+    planes = torch.empty((Nv, D // 32, 2, 32, 32), dtype=torch.float32, device=clips.device)
+    _lib.call("dkd_pack_clips_tf32", _p(clips), Nv, T, D, _p(planes), _stream())
+    return planes
+
+
+def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
+    """Exact clip-scale max/argmax over the P proposals via per-clip dots on the tcgen05
+    kind::tf32 path.  qn (M, D) normalised queries; clips: (Nv, T, D) fp32 or its pack_clips() form (5-D).
+    csr = (vid_ptr, q_list): only the listed (query, video) pairs, results in entry order; with
+    scatter = (slot, out_max, out_arg) entry e is written into the dense matrices at slot[e] instead."""
+    _chk(qn, torch.float32, "qn")
     _chk(prop_scale, torch.float32, "prop_scale")
+    planes = clips if clips.dim() == 5 else pack_clips(clips)
+    _chk(planes, torch.float32, "clip_planes")
     M, D = qn.shape
-    Nv, T, _ = clips.shape
+    Nv, P = prop_scale.shape
+    T = int(round(((8 * P + 1) ** 0.5 - 1) / 2))
+    if planes.shape[0] != Nv or planes.shape[1] * 32 != D or T * (T + 1) // 2 != P:
+        raise _lib.DkdError("clip_score_f32: clip planes / prop_scale / query shapes do not agree")
     dev = qn.device
     if csr is None:
         om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
         oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
-        _lib.call("dkd_clip_score_f32", _p(qn), M, _p(clips), _p(prop_scale), Nv, T, D, _p(om), _p(oa), Nv,
-                  None, None, _stream())
+        _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), Nv,
+                  None, None, None, _stream())
+        return om, oa
+    vid_ptr, q_list = csr
+    if scatter is not None:
+        slot, om, oa = scatter
+        _chk(om, torch.float32, "out_max")
+        _chk(oa, torch.int32, "out_arg")
     else:
-        vid_ptr, q_list = csr
+        slot = None
         E = q_list.numel()
         om = torch.empty((E,), dtype=torch.float32, device=dev)
         oa = torch.empty((E,), dtype=torch.int32, device=dev)
-        _lib.call("dkd_clip_score_f32", _p(qn), M, _p(clips), _p(prop_scale), Nv, T, D, _p(om), _p(oa), 0,
-                  _p(vid_ptr), _p(q_list), _stream())
+    _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), 0,
+              _p(vid_ptr), _p(q_list), _p(slot), _stream())
     return om, oa
 
 
@@ -156,13 +181,6 @@ def select_pairs_csr(gap, tau, cap=None):
     _lib.call("dkd_select_pairs_csr", _p(gap), M, Nv, Nv, tau, cap, _p(counts), _p(vid_ptr), _p(q_list), _p(slot),
               _stream())
     return vid_ptr, q_list, slot
-
-
-def scatter_pairs(cs, ck, csr, out_clip, out_key):
-    """Write the re-resolved (clip score, key clip) of the CSR entries back into the dense matrices."""
-    vid_ptr, q_list, slot = csr
-    _lib.call("dkd_scatter_pairs", _p(cs), _p(ck), _p(slot), _p(vid_ptr), vid_ptr.numel() - 1, slot.numel(),
-              _p(out_clip), _p(out_key), _stream())
 
 
 def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):

@@ -88,15 +88,23 @@ int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, i
                       int64_t ld_out, float* out_rows, const int32_t* vid_ptr,
                       const int32_t* q_list, void* stream);
 
-/* Exact fp32 clip-scale scores through per-clip dot products (SURVEY §7 "linearity"):
+/* Exact (fp32-grade) clip-scale scores through per-clip dot products (SURVEY §7 "linearity") on the
+ * tcgen05 tensor cores: kind::tf32 with operands split on the fly (x = hi + lo; lo.hi + hi.lo + hi.hi,
+ * fp32 accumulate in TMEM — error inside the summation-order noise of an fp32 einsum):
  *   d[m, n, i] = qn[m] . clips[n, i];  S[m, n, p(w,s)] = (sum_{i=s}^{s+w-1} d[m,n,i]) * prop_scale[n, p]
- *   out_max = max_p S, out_arg = first argmax_p.  Same CSR option as above. T <= 32.
+ *   out_max = max_p S, out_arg = first argmax_p.  T <= 32, D % 32 == 0, D <= 512, 16-byte aligned rows.
+ * clip_planes: the clips pre-packed by dkd_pack_clips_tf32 (once per corpus): per video the shared-memory image
+ * of the MMA's B operand (tf32 hi / lo planes, K-major 128-byte swizzle), dkd_clip_planes_bytes(Nv, D) bytes.
+ * Same CSR option as dkd_score_max_f32; with out_slot (CSR only) entry e is written to
+ * out_max[out_slot[e]] / out_arg[out_slot[e]] (scatter into a dense matrix) instead of out_max[e].
  * Replaces get_clip_scale_scores of the two-scale head, fp32 reference flavour.
  */
-int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const float* prop_scale,
+int64_t dkd_clip_planes_bytes(int32_t Nv, int32_t D);
+int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream);
+int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
                        int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
                        int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
-                       void* stream);
+                       const int32_t* out_slot, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * bf16 tcgen05/TMEM scoring GEMM with fused max/argmax epilogue (the hot kernel).
@@ -109,7 +117,7 @@ int dkd_clip_score_f32(const float* qn, int32_t M, const float* clips, const flo
  * cudaGetDriverEntryPoint) and passed as kernel parameters: no workspace.
  * out_gap (optional): best score minus the runner-up score of the same (query, video) — pairs whose
  * gap is below the bf16 noise floor have an ambiguous argmax and are re-resolved in fp32
- * (dkd_select_pairs_csr -> dkd_clip_score_f32 (CSR) -> dkd_scatter_pairs).  Scores carry the column
+ * (dkd_select_pairs_csr -> dkd_clip_score_f32 (CSR, out_slot)).  Scores carry the column
  * position in their 4 low mantissa bits inside the kernel: returned values are exact to 8 ulp.
  */
 int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
@@ -121,9 +129,6 @@ int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const ui
  * `cap` are dropped (size cap = M * Nv to make that impossible). */
 int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int64_t ld, float tau, int64_t cap,
                          int32_t* counts, int32_t* vid_ptr, int32_t* q_list, int32_t* slot, void* stream);
-/* out_clip[slot[e]] = cs[e], out_key[slot[e]] = ck[e] for e < min(vid_ptr[Nv], cap). */
-int dkd_scatter_pairs(const float* cs, const int32_t* ck, const int32_t* slot, const int32_t* vid_ptr,
-                      int32_t Nv, int64_t cap, float* out_clip, int32_t* out_key, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Key-clip-guided frame attention, query-independent table form:

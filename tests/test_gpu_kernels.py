@@ -111,20 +111,53 @@ def test_score_max_f32_no_mask_and_fully_masked_video(ops):
     assert (om2.cpu() - s_ref2).abs().max() <= FP32_TOL
 
 
-@pytest.mark.parametrize("M,Nv,D", [(70, 11, 384), (5, 3, 64)])
-def test_clip_score_f32(ops, M, Nv, D):
+@pytest.mark.parametrize("M,Nv,D,T", [(70, 11, 384, 32), (5, 3, 64, 32), (300, 160, 384, 32), (133, 7, 128, 8),
+                                      (260, 5, 512, 32)])
+def test_clip_score_f32(ops, M, Nv, D, T):
+    """Exact clip-scale scores (tcgen05 kind::tf32, split operands) vs the oracle's direct formulation."""
     frames, mask, lengths = synth.encoded_corpus(Nv, 128, D, seed=31)
     q = synth.encoded_queries(M, D, seed=32)
-    clips = O.downsample_clips(frames, lengths, 32)
+    clips = O.downsample_clips(frames, lengths, T)
     props = O.build_proposals(clips)
     s_ref, all_ref, k_ref = O.clip_scale_scores(q, props)
     qc, cc = _cuda(q, clips)
     qn, _ = ops.normalize_rows(qc)
     _, ps, _ = ops.build_proposals(cc, want_bf16=False)
     om, oa = ops.clip_score_f32(qn, cc, ps)
+    torch.cuda.synchronize()
     assert (om.cpu() - s_ref).abs().max() <= FP32_TOL
     ok, nbad = _argmax_ok(oa.cpu(), all_ref, k_ref, FP32_TOL)
     assert ok, f"{nbad} key-clip mismatches beyond fp32 ties"
+
+
+def test_clip_score_f32_csr_and_scatter(ops):
+    """CSR restriction (some videos with empty lists, ragged tiles) == the dense result at those pairs; the
+    scatter form writes them into dense matrices in place."""
+    M, Nv, D = 333, 23, 384
+    frames, mask, lengths = synth.encoded_corpus(Nv, 128, D, seed=33)
+    q = synth.encoded_queries(M, D, seed=34)
+    fc, lc, qc = _cuda(frames, lengths, q)
+    clips = ops.downsample_clips(fc, lc)
+    _, ps, _ = ops.build_proposals(clips, want_bf16=False)
+    qn, _ = ops.normalize_rows(qc)
+    dm, da = ops.clip_score_f32(qn, clips, ps)
+    g = torch.Generator().manual_seed(35)
+    gap = torch.rand(M, Nv, generator=g)
+    gap[:, 3] = 1.0                      # video 3: empty list
+    gap[:, 5] = 0.0                      # video 5: every query (3 tiles, last one ragged)
+    csr = ops.select_pairs_csr(gap.cuda(), 0.3)
+    vid_ptr, q_list, slot = csr
+    n_e = int(vid_ptr[-1].item())
+    assert n_e == int((gap < 0.3).sum())
+    cs, ck = ops.clip_score_f32(qn, clips, ps, csr=(vid_ptr, q_list))
+    sl = slot[:n_e].long()
+    assert torch.equal(cs[:n_e], dm.flatten()[sl]) and torch.equal(ck[:n_e], da.flatten()[sl])
+    out_m = torch.full((M, Nv), -7.0, device="cuda")
+    out_a = torch.full((M, Nv), -7, dtype=torch.int32, device="cuda")
+    ops.clip_score_f32(qn, clips, ps, csr=(vid_ptr, q_list), scatter=(slot, out_m, out_a))
+    sel = (gap < 0.3).cuda()
+    assert torch.equal(out_m[sel], dm[sel]) and torch.equal(out_a[sel], da[sel])
+    assert (out_m[~sel] == -7.0).all() and (out_a[~sel] == -7).all()
 
 
 @pytest.mark.parametrize("M,pad,Nv,R,D,masked", [

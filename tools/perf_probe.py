@@ -47,13 +47,14 @@ t = timeit(lambda: ops.frame_fuse(qb[:Nq], tb, om, oa, 0.7, 0.3, 0.7, fused=fuse
 t = timeit(lambda: ops.frame_fuse(qn[:Nq], tf, om, oa, 0.7, 0.3, 0.7, fused=fused, accumulate=False)); print(f"frame_fuse f32 {t:.3f} ms")
 t = timeit(lambda: ops.topk(fused, 128)); print(f"topk128 {t:.3f} ms")
 t = timeit(lambda: ops.topk(fused, 100)); print(f"topk100 {t:.3f} ms")
-t = timeit(lambda: ops.clip_score_f32(qn[:Nq], clips, ps), iters=2, warm=1); print(f"clip_score_f32 dense {t:.3f} ms")
+qsp = qn[:Nq]; csp = ops.pack_clips(clips)
+t = timeit(lambda: ops.clip_score_f32(qsp, csp, ps), iters=2, warm=1); print(f"clip_score_f32 dense {t:.3f} ms")
 fn32, _ = ops.normalize_rows(frames)
 t = timeit(lambda: ops.score_max_f32(qn[:Nq], fn32.view(Nv, L, D), None), iters=2, warm=1); print(f"score_max_f32 dense R=128 {t:.3f} ms")
 ts, ti = ops.topk(fused, 128)
 def resc():
     csr = ops.candidates_to_csr(ti, Nv)
-    cs, ck = ops.clip_score_f32(qn[:Nq], clips, ps, csr=csr[:2])
+    cs, ck = ops.clip_score_f32(qsp, csp, ps, csr=csr[:2])
     cand = torch.empty(Nq, 128, device=dev)
     ops.frame_fuse_csr(qn[:Nq], tf, cs, ck, csr, 0.7, 0.3, 0.7, cand, False)
     return ops.sort_candidates(cand, ti, 100)

@@ -227,6 +227,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     from dkd_b200 import engine, ops, _lib
     from dkd_b200.model import DLDKD

@@ -18,7 +18,7 @@ _F = c_float
 PROTOTYPES = {
     "dkd_version": [],
     "dkd_error_string": [_I],
-    "dkd_normalize_rows": [_P, _L, _I, _F, _P, _P, _L, _P],
+    "dkd_normalize_rows": [_P, _L, _I, _F, _P, _P, _P, _L, _P],
     "dkd_downsample_clips": [_P, _P, _I, _I, _I, _I, _P, _P],
     "dkd_build_proposals": [_P, _I, _I, _I, _P, _P, _P, _P],
     "dkd_score_max_f32": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P],

@@ -1,6 +1,8 @@
 // Corpus-side preparation kernels (query independent, run once per corpus / shard):
 // row normalisation + bf16 cast, clip downsample, clip-proposal builder, key-clip attention table.
 // All are HBM-bound streaming kernels; arithmetic is fp32.
+#include <cuda_fp16.h>
+
 #include "dkd_common.cuh"
 
 namespace dkd {
@@ -10,7 +12,7 @@ namespace dkd {
 // (method/model.py:318-319): x / max(||x||_2, eps) with a true division.
 __global__ void normalize_rows_kernel(const float* __restrict__ x, int64_t rows, int D, float eps,
                                       float* __restrict__ of32, __nv_bfloat16* __restrict__ obf,
-                                      int64_t rows_pad) {
+                                      __half* __restrict__ ohf, int64_t rows_pad) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -19,6 +21,7 @@ __global__ void normalize_rows_kernel(const float* __restrict__ x, int64_t rows,
       for (int d = lane; d < D; d += 32) {
         if (of32) of32[r * D + d] = 0.f;
         if (obf) obf[r * D + d] = __float2bfloat16(0.f);
+        if (ohf) ohf[r * D + d] = __float2half(0.f);
       }
       continue;
     }
@@ -34,6 +37,7 @@ __global__ void normalize_rows_kernel(const float* __restrict__ x, int64_t rows,
       float v = __fdiv_rn(xr[d], denom);
       if (of32) of32[r * D + d] = v;
       if (obf) obf[r * D + d] = __float2bfloat16(v);
+      if (ohf) ohf[r * D + d] = __float2half_rn(v);
     }
   }
 }
@@ -140,7 +144,7 @@ build_proposals_kernel(const float* __restrict__ clips, int T, int D,
 //  phase 2: softmax over valid frames (one warp per proposal row, accurate expf)
 //  phase 3: g[p][:] = sum_l a[p][l] * val[n][l][:]  — val streamed through smem in 64-feature
 //           chunks, each thread keeps 3 proposals x 4 features x (D/64) chunks in registers
-//  phase 4: row norm (16-lane reduction), write fp32 and bf16 rows.
+//  phase 4: row norm (16-lane reduction), write fp32 and fp16 rows.
 constexpr int kPC = 48;   // proposals per block (528 = 11 * 48)
 constexpr int kLmax = 128;
 
@@ -148,7 +152,7 @@ template <int kChunks>  // D = 64 * kChunks
 __global__ void __launch_bounds__(256)
 frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ val,
                         const int32_t* __restrict__ lengths, int L, int T, int D,
-                        float* __restrict__ table_f32, __nv_bfloat16* __restrict__ table_bf16) {
+                        float* __restrict__ table_f32, __half* __restrict__ table_f16) {
   extern __shared__ __align__(16) float smem_tab[];
   float (*sV)[64] = reinterpret_cast<float (*)[64]>(smem_tab);                        // kLmax x 64
   float (*sE)[33] = reinterpret_cast<float (*)[33]>(smem_tab + kLmax * 64);           // kLmax x 33
@@ -251,12 +255,12 @@ frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ v
         float4 o = make_float4(__fdiv_rn(acc[c][a][0], denom), __fdiv_rn(acc[c][a][1], denom),
                                __fdiv_rn(acc[c][a][2], denom), __fdiv_rn(acc[c][a][3], denom));
         if (table_f32) *reinterpret_cast<float4*>(&table_f32[ro + c * 64 + td * 4]) = o;
-        if (table_bf16) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        if (table_f16) {
+          __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&lo);
           pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(&table_bf16[ro + c * 64 + td * 4]) = pk;
+          *reinterpret_cast<uint2*>(&table_f16[ro + c * 64 + td * 4]) = pk;
         }
       }
     }
@@ -268,15 +272,16 @@ frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ v
 using namespace dkd;
 
 extern "C" int dkd_normalize_rows(const float* x, int64_t rows, int32_t D, float eps, float* out_f32,
-                                  uint16_t* out_bf16, int64_t rows_out_pad, void* stream) {
-  if (!x || rows < 0 || D <= 0 || (!out_f32 && !out_bf16)) return DKD_ERR_ARG;
+                                  uint16_t* out_bf16, uint16_t* out_f16, int64_t rows_out_pad, void* stream) {
+  if (!x || rows < 0 || D <= 0 || (!out_f32 && !out_bf16 && !out_f16)) return DKD_ERR_ARG;
   if (rows_out_pad < rows) rows_out_pad = rows;
   if (rows_out_pad == 0) return DKD_OK;
   const int wpb = 8;
   int64_t blocks = (rows_out_pad + wpb - 1) / wpb;
   if (blocks > 148 * 64) blocks = 148 * 64;
   normalize_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
-      x, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows_out_pad);
+      x, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<__half*>(out_f16),
+      rows_out_pad);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }
@@ -330,25 +335,25 @@ static int launch_frame_table(const float* E, const float* val, const int32_t* l
   DKD_CUDA_TRY(cudaFuncSetAttribute(frame_attn_table_kernel<kChunks>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   frame_attn_table_kernel<kChunks><<<grid, 256, smem, st>>>(E, val, lengths, L, T, D, tf,
-                                                            reinterpret_cast<__nv_bfloat16*>(tb));
+                                                            reinterpret_cast<__half*>(tb));
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }
 
 extern "C" int dkd_frame_attn_table(const float* E, const float* val, const int32_t* lengths, int32_t Nv,
                                     int32_t L, int32_t T, int32_t D, float* table_f32,
-                                    uint16_t* table_bf16, void* stream) {
-  if (!E || !val || !lengths || Nv < 0 || (!table_f32 && !table_bf16)) return DKD_ERR_ARG;
+                                    uint16_t* table_f16, void* stream) {
+  if (!E || !val || !lengths || Nv < 0 || (!table_f32 && !table_f16)) return DKD_ERR_ARG;
   if (L <= 0 || L > kLmax || T <= 0 || T > 32 || D % 64 != 0 || D > 512) return DKD_ERR_SHAPE;
   if (Nv == 0) return DKD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (D / 64) {
-    case 1: return launch_frame_table<1>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
-    case 2: return launch_frame_table<2>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
-    case 3: return launch_frame_table<3>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
-    case 4: return launch_frame_table<4>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
-    case 6: return launch_frame_table<6>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
-    case 8: return launch_frame_table<8>(E, val, lengths, Nv, L, T, D, table_f32, table_bf16, st);
+    case 1: return launch_frame_table<1>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
+    case 2: return launch_frame_table<2>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
+    case 3: return launch_frame_table<3>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
+    case 4: return launch_frame_table<4>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
+    case 6: return launch_frame_table<6>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
+    case 8: return launch_frame_table<8>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
   }
   return DKD_ERR_SHAPE;
 }

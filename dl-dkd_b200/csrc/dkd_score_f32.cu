@@ -6,6 +6,8 @@
 // in 32-wide chunks through shared memory (padded stride 36 words: conflict-free LDS.128),
 // 256 threads, each thread 2 query rows x kRows/8 corpus rows.  Two epilogues (max/argmax, store).
 // The clip-scale flavour lives in dkd_exact_tc.cu (tensor cores).
+#include <cuda_fp16.h>
+
 #include "dkd_common.cuh"
 
 namespace dkd {
@@ -175,26 +177,6 @@ struct RowLoader<float> {
     return acc;
   }
 };
-template <>
-struct RowLoader<__nv_bfloat16> {
-  static __device__ __forceinline__ float dot(const __nv_bfloat16* a, const __nv_bfloat16* b, int D, int sub) {
-    float acc = 0.f;
-    for (int d = sub * 8; d < D; d += 64) {
-      const uint4 x = *reinterpret_cast<const uint4*>(a + d);
-      const uint4 y = *reinterpret_cast<const uint4*>(b + d);
-      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
-      const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
-        acc = fmaf(xf.x, yf.x, acc);
-        acc = fmaf(xf.y, yf.y, acc);
-      }
-    }
-    return acc;
-  }
-};
-
 __device__ __forceinline__ float fuse_branch(float clip, float frame, float wc, float wf, float wb) {
   // torch: w_clip * clip + w_frame * frame ; numpy: w_branch * branch   (no FMA contraction)
   const float br = __fadd_rn(__fmul_rn(wc, clip), __fmul_rn(wf, frame));
@@ -228,6 +210,83 @@ frame_fuse_kernel(const TT* __restrict__ q, const TT* __restrict__ table,
       if (fused) {
         const float v = fuse_branch(clip[o], acc, wc, wf, wb);
         fused[o] = accumulate ? __fadd_rn(fused[o], v) : v;
+      }
+    }
+  }
+}
+
+// fp16 flavour of the dense gather (the approximate pass of the bf16 path).  An 8-lane group owns ONE query
+// for a chunk of videos: its 8 x (D/8) query halves stay in registers, per video only the key clip's table
+// row is fetched (768 B at D = 384: six 128-byte wavefronts per pair).  Products are formed and summed four
+// at a time in half2 (HFMA2), each 4-product partial sum is widened and accumulated in fp32.  Eight videos
+// are processed per step and their 8 x 8 lane partials reduced by a 7-shuffle transpose, so that lane j ends
+// with the frame score of video n0 + j: the (clip, key clip) loads and the fused stores are 32-byte runs.
+template <int kC>  // D = 64 * kC
+__global__ void __launch_bounds__(256)
+frame_fuse_h_kernel(const __half* __restrict__ q, const __half* __restrict__ table,
+                    const float* __restrict__ clip, const int32_t* __restrict__ key_clip, int M, int Nv,
+                    int P, int64_t ld, float wc, float wf, float wb, int accumulate, int vchunk,
+                    float* __restrict__ out_frame, float* __restrict__ fused) {
+  constexpr int D = 64 * kC;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int m = blockIdx.x * 32 + grp;
+  const bool live_m = m < M;
+  const int mm = live_m ? m : M - 1;
+  const int n_begin = blockIdx.y * vchunk;
+  const int n_end = min(Nv, n_begin + vchunk);
+  uint4 qv[kC];
+#pragma unroll
+  for (int i = 0; i < kC; ++i) qv[i] = *reinterpret_cast<const uint4*>(q + (int64_t)mm * D + 64 * i + 8 * sub);
+  const unsigned gmask = 0xffffffffu;                   // all groups of a warp run the same trip counts
+  for (int n0 = n_begin; n0 < n_end; n0 += 8) {
+    const int nj = n0 + sub;
+    const bool valid = nj < n_end;
+    const int64_t oj = (int64_t)mm * ld + (valid ? nj : n_begin);
+    int kk = key_clip[oj];
+    kk = kk < 0 ? 0 : (kk >= P ? P - 1 : kk);
+    float part[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = __shfl_sync(gmask, kk, j, 8);
+      const int n = min(n0 + j, n_end - 1);
+      const __half* row = table + ((int64_t)n * P + k) * D + 8 * sub;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < kC; ++i) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + 64 * i));
+        const __half2* tp = reinterpret_cast<const __half2*>(&t);
+        const __half2* qp = reinterpret_cast<const __half2*>(&qv[i]);
+        __half2 s2 = __hmul2(tp[0], qp[0]);
+        s2 = __hfma2(tp[1], qp[1], s2);
+        s2 = __hfma2(tp[2], qp[2], s2);
+        s2 = __hfma2(tp[3], qp[3], s2);
+        const float2 f = __half22float2(s2);
+        acc += f.x + f.y;
+      }
+      part[j] = acc;
+    }
+    // transpose-reduce: after the three rounds lane `sub` holds the total of pair `sub`
+    float r4[4], r2[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = (sub & 4) ? part[j] : part[j + 4];
+      const float keep = (sub & 4) ? part[j + 4] : part[j];
+      r4[j] = keep + __shfl_xor_sync(gmask, send, 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = (sub & 2) ? r4[j] : r4[j + 2];
+      const float keep = (sub & 2) ? r4[j + 2] : r4[j];
+      r2[j] = keep + __shfl_xor_sync(gmask, send, 2);
+    }
+    const float send = (sub & 1) ? r2[0] : r2[1];
+    const float keep = (sub & 1) ? r2[1] : r2[0];
+    const float frame = keep + __shfl_xor_sync(gmask, send, 1);
+    if (live_m && valid) {
+      if (out_frame) out_frame[oj] = frame;
+      if (fused) {
+        const float v = fuse_branch(clip[oj], frame, wc, wf, wb);
+        fused[oj] = accumulate ? __fadd_rn(fused[oj], v) : v;
       }
     }
   }
@@ -312,7 +371,7 @@ extern "C" int dkd_key_clip_dots(const float* key, const float* clips, int32_t N
   return launch_dots<32, EPI_STORE>(p, Nv, (L + kTM - 1) / kTM, (cudaStream_t)stream);
 }
 
-extern "C" int dkd_frame_fuse(const void* q, const void* table, int32_t is_bf16, const float* clip_scores,
+extern "C" int dkd_frame_fuse(const void* q, const void* table, int32_t is_f16, const float* clip_scores,
                               const int32_t* key_clip, int32_t M, int32_t Nv, int32_t P, int32_t D,
                               int64_t ld, float w_clip, float w_frame, float w_branch, int32_t accumulate,
                               float* out_frame, float* fused, void* stream) {
@@ -324,10 +383,27 @@ extern "C" int dkd_frame_fuse(const void* q, const void* table, int32_t is_bf16,
   dim3 grid((M + 31) / 32, (Nv + 7) / 8);
   if (grid.y > 65535) return DKD_ERR_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (is_bf16) {
-    frame_fuse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, clip_scores, key_clip, M, Nv, P, D, ld,
-        w_clip, w_frame, w_branch, accumulate, out_frame, fused);
+  if (is_f16) {
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(table)) & 15) return DKD_ERR_ALIGN;
+    const int vchunk = 32;                                 // videos per block: amortises the query registers
+    dim3 gh((M + 31) / 32, (Nv + vchunk - 1) / vchunk);
+    const __half* qh = (const __half*)q;
+    const __half* th = (const __half*)table;
+#define DKD_FF_H(C)                                                                                              \
+  frame_fuse_h_kernel<C><<<gh, 256, 0, st>>>(qh, th, clip_scores, key_clip, M, Nv, P, ld, w_clip, w_frame,       \
+                                             w_branch, accumulate, vchunk, out_frame, fused)
+    switch (D / 64) {
+      case 1: DKD_FF_H(1); break;
+      case 2: DKD_FF_H(2); break;
+      case 3: DKD_FF_H(3); break;
+      case 4: DKD_FF_H(4); break;
+      case 5: DKD_FF_H(5); break;
+      case 6: DKD_FF_H(6); break;
+      case 7: DKD_FF_H(7); break;
+      case 8: DKD_FF_H(8); break;
+      default: return DKD_ERR_SHAPE;
+    }
+#undef DKD_FF_H
   } else {
     frame_fuse_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)table, clip_scores,
                                                    key_clip, M, Nv, P, D, ld, w_clip, w_frame, w_branch,

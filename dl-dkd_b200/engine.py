@@ -19,7 +19,7 @@ HBM layout per branch (Nv videos, L frames, D features, T clips, P = T(T+1)/2 pr
   prop_scale (Nv, P)    fp32   1/(w*||mean||)                two-scale, exact + rescoring
   prop_b     (Nv*P, D)  bf16   L2-normalised proposals       two-scale GEMM B operand
   table_f    (Nv, P, D) fp32   normalised attention outputs  frame-scale, exact + rescoring
-  table_b    (Nv, P, D) bf16   same                          frame-scale, bf16
+  table_h    (Nv, P, D) fp16   same                          frame-scale gather of the bf16 path
 TVR shape, both branches: 2 x (428 + 214 + 107 + 5 + 884 + 1767 + 884 MB) = 8.6 GB of 180 GB.
 """
 from dataclasses import dataclass, field
@@ -42,7 +42,7 @@ class BranchData:
     prop_scale: Optional[torch.Tensor] = None
     prop_b: Optional[torch.Tensor] = None
     table_f: Optional[torch.Tensor] = None
-    table_b: Optional[torch.Tensor] = None
+    table_h: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -105,8 +105,8 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
             # W_k / W_v projections: plain library GEMMs in corpus preparation
             key = F.linear(fr, kw, kb).contiguous()
             val = F.linear(fr, vw, vb).contiguous()
-            bd.table_f, bd.table_b = ops.frame_attn_table(key, val, bd.clips, lengths, want_f32=True,
-                                                          want_bf16="bf16" in precisions)
+            bd.table_f, bd.table_h = ops.frame_attn_table(key, val, bd.clips, lengths, want_f32=True,
+                                                          want_f16="bf16" in precisions)
             del key, val
         pc.branches.append(bd)
     return pc
@@ -117,18 +117,21 @@ class PreparedQueries:
     M: int
     Mpad: int
     qn: List[torch.Tensor]   # per branch (M, D) fp32 normalised
-    qb: List[torch.Tensor]   # per branch (Mpad, D) bf16 normalised (or None)
+    qb: List[torch.Tensor]   # per branch (Mpad, D) bf16 normalised (or None): GEMM A operand
+    qh: List[torch.Tensor]   # per branch (Mpad, D) fp16 normalised (or None): frame-scale gather operand
 
 
 def prepare_queries(q_by_branch, want_bf16=True) -> PreparedQueries:
     M = q_by_branch[0].shape[0]
     Mpad = ops.round_up(max(M, 1), 256)  # 2 x 128: CTA pairs own two query tiles
-    qn, qb = [], []
+    qn, qb, qh = [], [], []
     for q in q_by_branch:
-        f, b = ops.normalize_rows(q.contiguous().float(), want_f32=True, want_bf16=want_bf16, rows_pad=Mpad)
+        f, b, h = ops.normalize_rows(q.contiguous().float(), want_f32=True, want_bf16=want_bf16, rows_pad=Mpad,
+                                     want_f16=True)
         qn.append(f[:M])
         qb.append(b)
-    return PreparedQueries(M=M, Mpad=Mpad, qn=qn, qb=qb)
+        qh.append(h)
+    return PreparedQueries(M=M, Mpad=Mpad, qn=qn, qb=qb, qh=qh)
 
 
 def _branch_weights(nb):
@@ -162,7 +165,7 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
     wbs = _branch_weights(nb)
     fused = None
     per = []
-    for bi, (bd, qn, qb) in enumerate(zip(pc.branches, pq.qn, pq.qb)):
+    for bi, (bd, qn, qb, qh) in enumerate(zip(pc.branches, pq.qn, pq.qb, pq.qh)):
         if precision == "exact":
             s_clip, k_clip = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale)
             q, tab = qn, bd.table_f
@@ -173,7 +176,7 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
                 ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2], scatter=(csr[2], s_clip, k_clip))
             else:
                 s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
-            q, tab = qb, bd.table_b
+            q, tab = qh, bd.table_h
         wb = wbs[bi] if nb == 2 else 1.0
         fused, fr = ops.frame_fuse(q, tab, s_clip, k_clip, w_clip, w_frame, wb, fused=fused, accumulate=bi > 0,
                                    want_frame=want_frame)

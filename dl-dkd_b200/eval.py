@@ -139,7 +139,7 @@ def compute_query2ctx_info(model, eval_dataset, opt, ctx_info):
             for bi in range(len(qs)):  # per-branch two-scale score = fused with branch weight 1
                 sub = engine.PreparedCorpus(Nv=pc.Nv, L=pc.L, D=pc.D, T=pc.T, id_base=pc.id_base, mask_u8=pc.mask_u8,
                                             lengths=pc.lengths, branches=[pc.branches[bi]], heads=pc.heads)
-                subq = engine.PreparedQueries(M=pq.M, Mpad=pq.Mpad, qn=[pq.qn[bi]], qb=[pq.qb[bi]])
+                subq = engine.PreparedQueries(M=pq.M, Mpad=pq.Mpad, qn=[pq.qn[bi]], qb=[pq.qb[bi]], qh=[pq.qh[bi]])
                 f, _ = engine.score_two_scale_head(sub, subq, precision, model.clip_scale_w, model.frame_scale_w)
                 outs[bi].append(f)
     inher = torch.cat(outs[0], dim=0).cpu().numpy().copy()

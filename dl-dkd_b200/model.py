@@ -249,7 +249,7 @@ class DLDKD(nn.Module):
         lengths = (feat_mask > 0).sum(dim=1).to(torch.int32).contiguous()
         clips = ops.downsample_clips(fr, lengths, self.map_size)
         tf, _ = ops.frame_attn_table(F.linear(fr, kw, kb).contiguous(), F.linear(fr, vw, vb).contiguous(), clips,
-                                     lengths, want_f32=True, want_bf16=False)
+                                     lengths, want_f32=True, want_f16=False)
         return tf
 
     def key_clip_guided_attention_in_inference(self, frame_feat, proposal_feat, feat_mask, max_index, branch=0):

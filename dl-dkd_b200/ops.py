@@ -41,16 +41,18 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-def normalize_rows(x, want_f32=True, want_bf16=False, rows_pad=None, eps=1e-12):
-    """F.normalize(x, dim=-1) (method/model.py:318-319) -> (fp32 | None, bf16 | None), each (rows_pad, D)."""
+def normalize_rows(x, want_f32=True, want_bf16=False, rows_pad=None, eps=1e-12, want_f16=False):
+    """F.normalize(x, dim=-1) (method/model.py:318-319) -> (fp32 | None, bf16 | None[, fp16]), each (rows_pad, D).
+    The fp16 copy (operand of the frame-scale gather) is returned as a third element when want_f16."""
     _chk(x, torch.float32, "x")
     D = x.shape[-1]
     rows = x.numel() // D
     rows_pad = rows if rows_pad is None else rows_pad
     of = torch.empty((rows_pad, D), dtype=torch.float32, device=x.device) if want_f32 else None
     ob = torch.empty((rows_pad, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    _lib.call("dkd_normalize_rows", _p(x), rows, D, eps, _p(of), _p(ob), rows_pad, _stream())
-    return of, ob
+    oh = torch.empty((rows_pad, D), dtype=torch.float16, device=x.device) if want_f16 else None
+    _lib.call("dkd_normalize_rows", _p(x), rows, D, eps, _p(of), _p(ob), _p(oh), rows_pad, _stream())
+    return (of, ob, oh) if want_f16 else (of, ob)
 
 
 def downsample_clips(frames, lengths, T=T_CLIPS):
@@ -183,8 +185,8 @@ def select_pairs_csr(gap, tau, cap=None):
     return vid_ptr, q_list, slot
 
 
-def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):
-    """Key-clip-guided attention outputs for every proposal of every video -> (Nv,P,D)."""
+def frame_attn_table(key, val, clips, lengths, want_f32=True, want_f16=True):
+    """Key-clip-guided attention outputs for every proposal of every video -> (fp32, fp16) (Nv,P,D)."""
     _chk(key, torch.float32, "key")
     _chk(val, torch.float32, "val")
     _chk(clips, torch.float32, "clips")
@@ -196,7 +198,7 @@ def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):
     E = torch.empty((Nv, L, T), dtype=torch.float32, device=dev)
     _lib.call("dkd_key_clip_dots", _p(key), _p(clips), Nv, L, T, D, _p(E), _stream())
     tf = torch.empty((Nv, P, D), dtype=torch.float32, device=dev) if want_f32 else None
-    tb = torch.empty((Nv, P, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    tb = torch.empty((Nv, P, D), dtype=torch.float16, device=dev) if want_f16 else None
     _lib.call("dkd_frame_attn_table", _p(E), _p(val), _p(lengths), Nv, L, T, D, _p(tf), _p(tb), _stream())
     return tf, tb
 
@@ -204,8 +206,8 @@ def frame_attn_table(key, val, clips, lengths, want_f32=True, want_bf16=True):
 def frame_fuse(q, table, clip_scores, key_clip, w_clip, w_frame, w_branch, fused=None, accumulate=False,
                want_frame=False):
     """frame[m,n] = q[m].table[n,key_clip[m,n]]; fused (+)= w_branch*(w_clip*clip + w_frame*frame)."""
-    is_bf16 = q.dtype == torch.bfloat16
-    _chk(q, torch.bfloat16 if is_bf16 else torch.float32, "q")
+    is_f16 = q.dtype == torch.float16
+    _chk(q, torch.float16 if is_f16 else torch.float32, "q")
     _chk(table, q.dtype, "table")
     _chk(key_clip, torch.int32, "key_clip")
     _chk(clip_scores, torch.float32, "clip_scores")
@@ -216,7 +218,7 @@ def frame_fuse(q, table, clip_scores, key_clip, w_clip, w_frame, w_branch, fused
     if fused is None:
         fused = torch.empty((M, Nv), dtype=torch.float32, device=dev)
         accumulate = False
-    _lib.call("dkd_frame_fuse", _p(q), _p(table), int(is_bf16), _p(clip_scores), _p(key_clip), M, Nv, P, D, Nv,
+    _lib.call("dkd_frame_fuse", _p(q), _p(table), int(is_f16), _p(clip_scores), _p(key_clip), M, Nv, P, D, Nv,
               w_clip, w_frame, w_branch, int(accumulate), _p(fr), _p(fused), _stream())
     return fused, fr
 

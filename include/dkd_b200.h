@@ -18,7 +18,8 @@
  *   - "rows per video" R: the scoring kernels see the corpus as Nv * R rows of D
  *     features; R = L (frames, reference path) or R = P = T(T+1)/2 (clip proposals).
  *
- * All arithmetic types: fp32 scores, int32 indices, bf16 (uint16_t storage) GEMM operands.
+ * All arithmetic types: fp32 scores, int32 indices, bf16 (uint16_t storage) GEMM operands, fp16 (uint16_t
+ * storage) operands of the approximate frame-scale gather.
  */
 #ifndef DKD_B200_H_
 #define DKD_B200_H_
@@ -42,14 +43,14 @@ int dkd_version(void);
 const char* dkd_error_string(int code);
 
 /* ---------------------------------------------------------------------------------------
- * Row preparation: L2-normalise every D-vector (x / max(||x||, eps)), write fp32 and/or bf16.
+ * Row preparation: L2-normalise every D-vector (x / max(||x||, eps)), write fp32 and/or bf16 and/or fp16.
  * Replaces F.normalize(modularied_query) / F.normalize(context_feat), method/model.py:318-319
  * (hoisted out of the per-query-batch loop of method/eval.py:188-208).
- * rows_out_pad >= rows: extra output rows are zero-filled (GEMM M padding). Either output may
- * be NULL.
+ * rows_out_pad >= rows: extra output rows are zero-filled (GEMM M padding). Any output may be NULL
+ * (bf16: GEMM operands; fp16: operands of the frame-scale gather).
  */
-int dkd_normalize_rows(const float* x, int64_t rows, int32_t D, float eps,
-                       float* out_f32, uint16_t* out_bf16, int64_t rows_out_pad, void* stream);
+int dkd_normalize_rows(const float* x, int64_t rows, int32_t D, float eps, float* out_f32,
+                       uint16_t* out_bf16, uint16_t* out_f16, int64_t rows_out_pad, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Clip downsample: encoded frames (Nv, L, D) + valid lengths -> (Nv, T, D) clip features with
@@ -137,22 +138,23 @@ int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int64_t ld, fl
  *   a               = softmax over valid frames l < lengths[n]
  *   g[n, p]         = sum_l a_l * val[n, l];   table = g / max(||g||, 1e-12)
  * key/val (Nv, L, D) fp32 are the W_k / W_v projections of the encoded frames.
- * Outputs (either may be NULL): table_f32, table_bf16 (Nv, P, D). L <= 128, T <= 32, D % 64 == 0,
+ * Outputs (either may be NULL): table_f32, table_f16 (Nv, P, D; IEEE half). L <= 128, T <= 32, D % 64 == 0,
  * D <= 512.  E is a caller-provided scratch of Nv*L*T floats.
  */
 int dkd_key_clip_dots(const float* key, const float* clips, int32_t Nv, int32_t L, int32_t T,
                       int32_t D, float* E, void* stream);
 int dkd_frame_attn_table(const float* E, const float* val, const int32_t* lengths, int32_t Nv,
-                         int32_t L, int32_t T, int32_t D, float* table_f32, uint16_t* table_bf16,
+                         int32_t L, int32_t T, int32_t D, float* table_f32, uint16_t* table_f16,
                          void* stream);
 
 /* Frame-scale score + branch fusion (cross-branch weights method/eval.py:254):
  *   frame[m, n]  = q[m] . table[n, key_clip[m, n]]
  *   branch[m, n] = fl(w_clip * clip[m, n]) + fl(w_frame * frame[m, n])
  *   fused[m, n]  = accumulate ? fused[m, n] + fl(w_branch * branch) : fl(w_branch * branch)
- * q/table both fp32 (is_bf16 = 0) or both bf16 (is_bf16 = 1).  out_frame / fused may be NULL.
+ * q/table both fp32 (is_f16 = 0: exact path) or both fp16 (is_f16 = 1: half2 FMA in chunks of 4 products,
+ * fp32 accumulation across chunks; D % 64 == 0).  out_frame / fused may be NULL.
  */
-int dkd_frame_fuse(const void* q, const void* table, int32_t is_bf16, const float* clip_scores,
+int dkd_frame_fuse(const void* q, const void* table, int32_t is_f16, const float* clip_scores,
                    const int32_t* key_clip, int32_t M, int32_t Nv, int32_t P, int32_t D,
                    int64_t ld, float w_clip, float w_frame, float w_branch, int32_t accumulate,
                    float* out_frame, float* fused, void* stream);

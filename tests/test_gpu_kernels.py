@@ -226,7 +226,7 @@ def test_frame_attn_table(ops, Nv, L, D):
     kc, vc, cc, lc = _cuda(key, val, clips, lengths)
     tf, tb = ops.frame_attn_table(kc, vc, cc, lc)
     assert (tf.cpu() - ref).abs().max() <= 5e-6
-    assert (tb.float().cpu() - ref).abs().max() <= 2 ** -8
+    assert tb.dtype == torch.float16 and (tb.float().cpu() - ref).abs().max() <= 2 ** -11
 
 
 def test_two_scale_branch_exact_path(ops):
@@ -249,6 +249,28 @@ def test_two_scale_branch_exact_path(ops):
     assert same.float().mean() > 0.999
     assert (fr.cpu()[same] - ref["frame"][same]).abs().max() <= 5e-6
     assert (fused.cpu()[same] - ref["branch"][same]).abs().max() <= 5e-6
+
+
+@pytest.mark.parametrize("M,Nv,D", [(77, 45, 384), (33, 7, 64), (260, 100, 512)])
+def test_frame_fuse_fp16_gather(ops, M, Nv, D):
+    """The fp16 dense gather (half2 products, fp32 accumulation across 4-product chunks) against the fp32 gather
+    on the same table: operand rounding 2^-12 relative + chunk rounding -> well inside 2e-4; ragged M / Nv tails."""
+    P = 528
+    g = torch.Generator().manual_seed(123)
+    table = F.normalize(torch.randn(Nv, P, D, generator=g), dim=-1)
+    q = F.normalize(torch.randn(M, D, generator=g), dim=-1)
+    clip = torch.rand(M, Nv, generator=g)
+    key = torch.randint(0, P, (M, Nv), generator=g, dtype=torch.int32)
+    tc, qc, cc, kc = _cuda(table, q, clip, key)
+    ref_fused, ref_fr = ops.frame_fuse(qc, tc, cc, kc, 0.7, 0.3, 0.7, want_frame=True)
+    want = (q[:, None, :] * table[torch.arange(Nv)[None, :], key.long()]).sum(-1)
+    assert (ref_fr.cpu() - want).abs().max() <= 2e-6
+    fused = torch.full((M, Nv), 0.25, device="cuda")
+    got_fused, got_fr = ops.frame_fuse(qc.half(), tc.half(), cc, kc, 0.7, 0.3, 0.7, fused=fused, accumulate=True,
+                                       want_frame=True)
+    torch.cuda.synchronize()
+    assert (got_fr - ref_fr).abs().max().item() <= 2e-4
+    assert (got_fused - (ref_fused + 0.25)).abs().max().item() <= 2e-4
 
 
 def test_fuse_scores_bit_exact(ops):
@@ -323,7 +345,7 @@ def test_candidate_rescoring_plumbing(ops):
     qn, _ = ops.normalize_rows(qc)
     s_clip, k_clip = ops.clip_score_f32(qn, clips, ps)
     tf, _ = ops.frame_attn_table(F.linear(frames, kw, kb).cuda(), F.linear(frames, vw, vb).cuda(), clips, lc,
-                                 want_bf16=False)
+                                 want_f16=False)
     fused, _ = ops.frame_fuse(qn, tf, s_clip, k_clip, 0.7, 0.3, 1.0)
     ts, ti = ops.topk(fused, K)
     # perturb candidate order, then rescore

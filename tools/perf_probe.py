@@ -24,7 +24,7 @@ frames = torch.randn(Nv, L, D, device=dev) + 0.6 * torch.randn(Nv, 1, D, device=
 lengths = torch.full((Nv,), L, dtype=torch.int32, device=dev)
 q = torch.randn(Nq, D, device=dev)
 Mpad = ops.round_up(Nq, 128)
-qn, qb = ops.normalize_rows(q, True, True, rows_pad=Mpad)
+qn, qb, qh = ops.normalize_rows(q, True, True, rows_pad=Mpad, want_f16=True)
 clips = ops.downsample_clips(frames, lengths)
 t = timeit(lambda: ops.downsample_clips(frames, lengths)); print(f"downsample_clips {t:.3f} ms")
 pb, ps, _ = ops.build_proposals(clips)
@@ -43,7 +43,7 @@ t2 = timeit(fn2, iters=10, warm=3)
 print(f"score_max_bf16 R=128: {t2:.3f} ms  {2.0*Nq*Nv*L*D/t2/1e9:.1f} TFLOP/s")
 fn(); 
 fused = torch.empty(Nq, Nv, device=dev)
-t = timeit(lambda: ops.frame_fuse(qb[:Nq], tb, om, oa, 0.7, 0.3, 0.7, fused=fused, accumulate=False)); print(f"frame_fuse bf16 {t:.3f} ms  gather {Nq*Nv*D*2/t/1e6:.1f} GB/s")
+t = timeit(lambda: ops.frame_fuse(qh[:Nq], tb, om, oa, 0.7, 0.3, 0.7, fused=fused, accumulate=False)); print(f"frame_fuse fp16 {t:.3f} ms  gather {Nq*Nv*D*2/t/1e6:.1f} GB/s")
 t = timeit(lambda: ops.frame_fuse(qn[:Nq], tf, om, oa, 0.7, 0.3, 0.7, fused=fused, accumulate=False)); print(f"frame_fuse f32 {t:.3f} ms")
 t = timeit(lambda: ops.topk(fused, 128)); print(f"topk128 {t:.3f} ms")
 t = timeit(lambda: ops.topk(fused, 100)); print(f"topk100 {t:.3f} ms")

@@ -71,10 +71,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// hi = tf32(x) rounded to nearest; lo = x - hi exactly (<= 13 significant bits).  The tensor core reads only the
-// tf32 part of lo (drops its low 13 bits: <= 2^-21 |x|, sign-symmetric because hi is rounded to nearest).
+// hi = tf32(x) rounded to nearest (ties away from zero: add half an ulp to the magnitude bits, clear the low 13
+// bits — cvt.rna.tf32.f32 without its inf/nan handling; operands are finite L2-normalised features);
+// lo = x - hi exactly (<= 13 significant bits).  The tensor core reads only the tf32 part of lo (drops its low
+// 13 bits: <= 2^-21 |x|, sign-symmetric because hi is rounded to nearest).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
@@ -117,7 +119,8 @@ template <bool kT32, int kXRing>
 __global__ void __launch_bounds__(kXThreads, 1)
 clip_exact_umma_kernel(const ExactParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
-  __shared__ float s_scale[2][528];   // prop_scale row of the current video (scan warps, double buffered)
+  __shared__ __align__(16) float s_scale[2][32 * 32];   // prop_scale of the current video as [w - 1][s] (scan warps,
+                                                        // double buffered): 16-byte loads at compile-time offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_x) + 1023) & ~(uintptr_t)1023);
   const int num_kb = p.D / kXKB;
   const uint32_t b_buf_bytes = (uint32_t)num_kb * 2u * kXBPlane;
@@ -330,7 +333,15 @@ clip_exact_umma_kernel(const ExactParams p) {
       float* sc = s_scale[vi & 1u];
       // the buffer was last read two videos ago; the barrier below (one per video) orders those reads before
       // these writes: a warp can be at most one video ahead of the slowest one
-      for (int i = stid; i < P; i += kXScanWarps * 32) sc[i] = __ldg(p.scale + (int64_t)n * P + i);
+      {
+        const float* gsc = p.scale + (int64_t)n * P;
+        const int s_ = stid & 31;
+        int base = 0;                                               // p(w, 0)
+        for (int w = 1; w <= T; ++w) {
+          if ((w & 3) == (stid >> 5) && s_ + w <= T) sc[(w - 1) * 32 + s_] = __ldg(gsc + base + s_);
+          base += T - w + 1;
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kXScanWarps * 32) : "memory");
       ++vi;
       for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
@@ -352,12 +363,16 @@ clip_exact_umma_kernel(const ExactParams p) {
         for (int k = 0; k < 8; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
 #pragma unroll
         for (int w = 1; w <= 32; ++w) {
+          float scw[32];
+#pragma unroll
+          for (int s4 = 0; s4 + w <= 32; s4 += 4)
+            *reinterpret_cast<float4*>(&scw[s4]) = *reinterpret_cast<const float4*>(&sc[(w - 1) * 32 + s4]);
 #pragma unroll
           for (int s = 0; s + w <= 32; ++s) {
             run[s] = (w == 1) ? d[s] : __fadd_rn(run[s], d[s + w - 1]);
             if (kT32 || s + w <= T) {
               const int pi = kT32 ? ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s) : ((w - 1) * T - ((w - 1) * (w - 2)) / 2 + s);
-              const float v = __fmul_rn(run[s], sc[pi]);
+              const float v = __fmul_rn(run[s], scw[s]);
               if (v > bv[s & 7]) { bv[s & 7] = v; bi[s & 7] = pi; }
             }
           }

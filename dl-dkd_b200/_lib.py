@@ -22,6 +22,9 @@ PROTOTYPES = {
     "dkd_downsample_clips": [_P, _P, _I, _I, _I, _I, _P, _P],
     "dkd_build_proposals": [_P, _I, _I, _I, _P, _P, _P, _P],
     "dkd_score_max_f32": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P, _P],
+    "dkd_row_planes_bytes": [_I, _I, _I],
+    "dkd_pack_rows_tf32": [_P, _I, _I, _I, _P, _P],
+    "dkd_score_max_exact": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P],
     "dkd_clip_planes_bytes": [_I, _I],
     "dkd_pack_clips_tf32": [_P, _I, _I, _I, _P, _P],
     "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P],
@@ -39,7 +42,7 @@ PROTOTYPES = {
     "dkd_scatter_fuse": [_P, _P, _F, _F, _P, _P, _I, _L, _P, _P],
     "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
 }
-_RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64}
+_RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64, "dkd_row_planes_bytes": c_int64}
 
 _lib = None
 

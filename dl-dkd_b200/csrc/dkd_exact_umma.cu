@@ -35,10 +35,10 @@ constexpr int kXStagers = 4 * 32;            // stager threads that fill one A s
 constexpr int kXMmaWarp = kXScanWarps + kXStageWarps;
 constexpr int kXLoadWarp = kXMmaWarp + 1;   // B-operand loader (cp.async.bulk of the pre-packed clip planes)
 constexpr int kXThreads = (kXLoadWarp + 1) * 32;
-constexpr int kXStages = 7;               // A ring stages in TMEM: 64 + 7 * 64 = 512 columns
+constexpr int kXMaxAStages = 7;             // A ring stages in TMEM: (512 - 2 x accumulator width) / 64
+constexpr int kXBStages = 3;                // rows mode: B ring stages in shared memory
 constexpr uint32_t kXBPlane = 32 * 128;      // 4 KB : 32 clips x 128 B
 constexpr int kXTmemCols = 512;
-constexpr uint32_t kXACol0 = 64;            // first A-ring column
 constexpr uint32_t kXRowPitch = 128;        // staged fp32 row of one K block; 16-byte chunk c of row r sits at
                                             // chunk c ^ ((r & 1) << 2): conflict-free cp.async writes and LDS.128 reads
 constexpr uint32_t kXSlotBytes = 32 * kXRowPitch;
@@ -49,13 +49,15 @@ struct ExactParams {
   const float* planes; const float* scale;
   int Nv, T, D;
   int b_bufs;
+  int R, Npad;                 // rows mode: rows per video, padded to a multiple of 16 (UMMA N)
+  const uint8_t* mask;         // rows mode: (Nv, R) or null
   float* out_max; int32_t* out_arg; int64_t ld_out;
   const int32_t* vid_ptr; const int32_t* q_list; const int32_t* out_slot;
 };
 
 struct __align__(8) ExactCtl {
-  uint64_t a_full[kXStages], a_empty[kXStages];
-  uint64_t b_full[2], b_empty[2];
+  uint64_t a_full[kXMaxAStages], a_empty[kXMaxAStages];
+  uint64_t b_full[kXBStages], b_empty[kXBStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
@@ -115,26 +117,31 @@ __device__ __forceinline__ void video_range(const ExactParams& p, int n, int& e0
   else { e0 = 0; count = p.M; }
 }
 
-template <bool kT32, int kXRing>
+// kMode 0: clip windows (B = the video's 32 clips, resident; scan = T(T+1)/2 window cosines).
+// kMode 1: rows max (B = the video's R <= 128 rows, streamed per K block through a ring; scan = masked max).
+template <int kMode, bool kT32, int kXRing>
 __global__ void __launch_bounds__(kXThreads, 1)
-clip_exact_umma_kernel(const ExactParams p) {
+exact_umma_kernel(const ExactParams p) {
+  constexpr int kDW = kMode == 0 ? 32 : 128;                    // accumulator columns per TMEM buffer
+  constexpr uint32_t kXACol0 = 2 * kDW;                         // first A-ring column
+  constexpr int kXStages = (kXTmemCols - 2 * kDW) / 64;         // A ring stages: 7 / 4
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
   __shared__ __align__(16) float s_scale[2][32 * 32];   // prop_scale of the current video as [w - 1][s] (scan warps,
                                                         // double buffered): 16-byte loads at compile-time offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_x) + 1023) & ~(uintptr_t)1023);
   const int num_kb = p.D / kXKB;
-  const uint32_t b_buf_bytes = (uint32_t)num_kb * 2u * kXBPlane;
-  uint8_t* sB = smem;                                           // [buf][kb][plane] x 4 KB
-  uint8_t* sS = sB + (size_t)p.b_bufs * b_buf_bytes;            // [stager warp][slot][32 rows] x 192 B
+  // mode 0: [buf][kb][plane] x 4 KB, one buffer per video; mode 1: [stage][plane] x Npad x 128 B, one stage per K block
+  const uint32_t b_buf_bytes = kMode == 0 ? (uint32_t)num_kb * 2u * kXBPlane : 2u * (uint32_t)p.Npad * 128u;
+  uint8_t* sB = smem;
+  uint8_t* sS = sB + (size_t)(kMode == 0 ? p.b_bufs : kXBStages) * b_buf_bytes;   // [stager warp][slot][32 rows] x 128 B
   ExactCtl* ctl = reinterpret_cast<ExactCtl*>(sS + (size_t)kXStageWarps * kXRing * kXSlotBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bufs = (uint32_t)p.b_bufs;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXStages; ++i) { mbar_init(&ctl->a_full[i], kXStagers); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < kXBStages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl->b_full[i], 1);
-      mbar_init(&ctl->b_empty[i], 1);
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], kXScanWarps);
     }
@@ -257,50 +264,74 @@ clip_exact_umma_kernel(const ExactParams p) {
   } else if (warp == kXLoadWarp) {
     // ===================== B loader =====================
     if (lane == 0) {
-      uint32_t vi = 0;
+      uint32_t vi = 0, itb = 0;
       for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
         int e0, count;
         video_range(p, n, e0, count);
         if (count <= 0) continue;
-        const uint32_t bb = vi % b_bufs;
-        mbar_wait(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u);
-        ++vi;
-        mbar_expect_tx(&ctl->b_full[bb], b_buf_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * b_buf_bytes;
-        for (int kb = 0; kb < num_kb; ++kb)                       // 8 KB per K block: hi plane, lo plane
-          bulk_load(sB + (size_t)bb * b_buf_bytes + (size_t)kb * 2 * kXBPlane, src + (size_t)kb * 2 * kXBPlane,
-                    2 * kXBPlane, &ctl->b_full[bb]);
+        if (kMode == 0) {
+          const uint32_t bb = vi % b_bufs;
+          mbar_wait(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u);
+          ++vi;
+          mbar_expect_tx(&ctl->b_full[bb], b_buf_bytes);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * b_buf_bytes;
+          for (int kb = 0; kb < num_kb; ++kb)                     // 8 KB per K block: hi plane, lo plane
+            bulk_load(sB + (size_t)bb * b_buf_bytes + (size_t)kb * 2 * kXBPlane, src + (size_t)kb * 2 * kXBPlane,
+                      2 * kXBPlane, &ctl->b_full[bb]);
+        } else {
+          // every tile of the video streams the video's row planes again (L2 resident): one stage per K block
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * num_kb * b_buf_bytes;
+          for (int t0 = 0; t0 < count; t0 += kXRows) {
+            for (int kb = 0; kb < num_kb; ++kb, ++itb) {
+              const uint32_t bs = itb % (uint32_t)kXBStages;
+              mbar_wait(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u);
+              mbar_expect_tx(&ctl->b_full[bs], b_buf_bytes);
+              bulk_load(sB + (size_t)bs * b_buf_bytes, src + (size_t)kb * b_buf_bytes, b_buf_bytes, &ctl->b_full[bs]);
+            }
+          }
+        }
       }
     }
   } else if (warp == kXMmaWarp) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_tf32(32, kXRows);
+    const int nb = kMode == 0 ? 32 : p.Npad;                    // UMMA N
+    const uint32_t idesc = make_idesc_tf32(nb, kXRows);
+    const uint32_t b_plane = (uint32_t)nb * 128u;               // bytes of one plane of one K block
     const bool elected = elect_one();
     const uint64_t bdesc0 = make_smem_desc(smem_u32(sB));
-    uint32_t it = 0, vi = 0, tc = 0;
+    uint32_t it = 0, vi = 0, tc = 0, itb = 0;
     for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
       int e0, count;
       video_range(p, n, e0, count);
       if (count <= 0) continue;
-      const uint32_t bb = vi % b_bufs;
-      mbar_wait(&ctl->b_full[bb], (vi / b_bufs) & 1u);
-      ++vi;
-      const uint64_t bdesc_v = bdesc0 + (uint64_t)((bb * b_buf_bytes) >> 4);
+      uint32_t bb = 0;
+      if (kMode == 0) {
+        bb = vi % b_bufs;
+        mbar_wait(&ctl->b_full[bb], (vi / b_bufs) & 1u);
+        ++vi;
+      }
       for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
         const uint32_t buf = tc & 1u;
         mbar_wait(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 32u;
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)kDW;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t stage = it % (uint32_t)kXStages;
           const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
+          uint32_t bs = 0;
+          if (kMode == 1) {
+            bs = itb % (uint32_t)kXBStages;
+            mbar_wait(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u);
+            ++itb;
+          }
           mbar_wait(&ctl->a_full[stage], phase);
           tc_fence_after();
           if (elected) {
             const uint32_t a_hi = tmem_base + kXACol0 + stage * 64u;
             const uint32_t a_lo = a_hi + 32u;
-            const uint64_t b_hi = bdesc_v + (uint64_t)(((uint32_t)kb * 2u * kXBPlane) >> 4);
-            const uint64_t b_lo = b_hi + (uint64_t)(kXBPlane >> 4);
+            const uint64_t b_hi = kMode == 0 ? bdesc0 + (uint64_t)((bb * b_buf_bytes + (uint32_t)kb * 2u * b_plane) >> 4)
+                                             : bdesc0 + (uint64_t)((bs * b_buf_bytes) >> 4);
+            const uint64_t b_lo = b_hi + (uint64_t)(b_plane >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {   // 8 tf32 per MMA: 8 TMEM columns of A, 32 B (+2 x 16 B) of the B swizzle row
               umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);   // small terms first
@@ -308,17 +339,20 @@ clip_exact_umma_kernel(const ExactParams p) {
               umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
             }
             umma_commit(&ctl->a_empty[stage]);
+            if (kMode == 1) umma_commit(&ctl->b_empty[bs]);
           }
           __syncwarp();
         }
         if (elected) umma_commit(&ctl->tmem_full[buf]);
         __syncwarp();
       }
-      if (elected) umma_commit(&ctl->b_empty[bb]);
-      __syncwarp();
+      if (kMode == 0) {
+        if (elected) umma_commit(&ctl->b_empty[bb]);
+        __syncwarp();
+      }
     }
-  } else {
-    // ===================== scan =====================
+  } else if constexpr (kMode == 0) {
+    // ===================== scan: clip windows =====================
     // Thread = tile row.  Windows are visited w-major, so inside each of the 8 independent running maxima
     // (start class s & 7) proposal indices increase and strict > keeps the first maximum; the final merge
     // compares (value desc, index asc).
@@ -349,7 +383,7 @@ clip_exact_umma_kernel(const ExactParams p) {
         mbar_wait(&ctl->tmem_full[buf], (tc >> 1) & 1u);
         tc_fence_after();
         uint32_t raw[32];
-        tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 32u, raw);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)kDW, raw);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -389,6 +423,49 @@ clip_exact_umma_kernel(const ExactParams p) {
         }
       }
     }
+  } else {
+    // ===================== scan: masked max over the rows =====================
+    // Thread = tile row: its R dots arrive as 32-column TMEM loads; masked rows score exactly -1e10
+    // (mask_logits, method/model.py:444-445); strict > in row order keeps the first maximum (torch.max).
+    const int quarter = warp;
+    uint32_t tc = 0;
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int e0, count;
+      video_range(p, n, e0, count);
+      if (count <= 0) continue;
+      const uint8_t* mrow = p.mask ? p.mask + (int64_t)n * p.R : nullptr;
+      for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(&ctl->tmem_full[buf], (tc >> 1) & 1u);
+        tc_fence_after();
+        float bv = -INFINITY;
+        int bi = 0;
+        for (int c0 = 0; c0 < p.R; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)kDW + (uint32_t)c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int r = c0 + j;
+            if (r < p.R) {
+              float v = __uint_as_float(raw[j]);
+              if (mrow && __ldg(mrow + r) == 0) v = DKD_MASKED_SCORE;
+              if (v > bv) { bv = v; bi = r; }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+        const int r = t0 + quarter * 32 + lane;
+        if (r < count) {
+          const int64_t o = p.out_slot ? (int64_t)p.out_slot[e0 + r]
+                                       : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n);
+          p.out_max[o] = bv;
+          if (p.out_arg) p.out_arg[o] = bi;
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -399,28 +476,30 @@ clip_exact_umma_kernel(const ExactParams p) {
   }
 }
 
-// Pre-pack the clips of every video into the shared-memory image of the exact kernel's B operand:
-// planes[n][kb][plane][32 rows x 128 B, SWIZZLE_128B], plane 0 = tf32 hi, 1 = tf32 lo, rows >= T zero, features
+// Pre-pack the rows of every video (clips, or frames) into the shared-memory image of the exact kernels' B operand:
+// planes[n][kb][plane][rpad rows x 128 B, SWIZZLE_128B], plane 0 = tf32 hi, 1 = tf32 lo, rows >= R zero, features
 // of a K block permuted like the A operand (feature 16c + 4t + 2b + e at position 16c + 8b + 2t + e).
-__global__ void pack_clips_tf32_kernel(const float* __restrict__ clips, int T, int D, float* __restrict__ planes) {
+__global__ void pack_rows_tf32_kernel(const float* __restrict__ x, int R, int rpad, int D, float* __restrict__ planes) {
   const int n = blockIdx.x;
   const int num_kb = D / kXKB;
-  uint8_t* dst = reinterpret_cast<uint8_t*>(planes) + (size_t)n * num_kb * 2 * kXBPlane;
-  for (int i = threadIdx.x; i < num_kb * 256; i += blockDim.x) {
-    const int kb = i >> 8, r = (i >> 3) & 31, c8 = i & 7;         // float4 c8: features 4 c8 .. 4 c8 + 3
+  const uint32_t plane_bytes = (uint32_t)rpad * 128u;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(planes) + (size_t)n * num_kb * 2 * plane_bytes;
+  for (int i = threadIdx.x; i < num_kb * rpad * 8; i += blockDim.x) {
+    const int kb = i / (rpad * 8), rem = i - kb * rpad * 8;
+    const int r = rem >> 3, c8 = rem & 7;                           // float4 c8: features 4 c8 .. 4 c8 + 3
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) v = *reinterpret_cast<const float4*>(clips + ((int64_t)n * T + r) * D + kb * kXKB + c8 * 4);
+    if (r < R) v = *reinterpret_cast<const float4*>(x + ((int64_t)n * R + r) * D + kb * kXKB + c8 * 4);
     uint2 h0, l0, h1, l1;
     split_tf32(v.x, h0.x, l0.x); split_tf32(v.y, h0.y, l0.y); split_tf32(v.z, h1.x, l1.x); split_tf32(v.w, h1.y, l1.y);
     const int cc = c8 >> 2, tt = c8 & 3;
     const int p0 = 16 * cc + 2 * tt;                                // b = 0; b = 1 is 8 positions further
-    uint8_t* row0 = dst + (size_t)(kb * 2) * kXBPlane;
+    uint8_t* row0 = dst + (size_t)(kb * 2) * plane_bytes;
     uint8_t* d0 = row0 + sw128_off(r, p0 >> 2) + (p0 & 3) * 4;
     uint8_t* d1 = row0 + sw128_off(r, (p0 + 8) >> 2) + (p0 & 3) * 4;
     *reinterpret_cast<uint2*>(d0) = h0;
     *reinterpret_cast<uint2*>(d1) = h1;
-    *reinterpret_cast<uint2*>(d0 + kXBPlane) = l0;
-    *reinterpret_cast<uint2*>(d1 + kXBPlane) = l1;
+    *reinterpret_cast<uint2*>(d0 + plane_bytes) = l0;
+    *reinterpret_cast<uint2*>(d1 + plane_bytes) = l1;
   }
 }
 
@@ -428,19 +507,89 @@ __global__ void pack_clips_tf32_kernel(const float* __restrict__ clips, int T, i
 
 using namespace dkd;
 
+static int row_pad(int R, int clip_mode) { return clip_mode ? 32 : ((R + 15) / 16) * 16; }
+
 extern "C" int64_t dkd_clip_planes_bytes(int32_t Nv, int32_t D) {
   if (Nv < 0 || D <= 0 || D % kXKB != 0) return -1;
   return (int64_t)Nv * (D / kXKB) * 2 * kXBPlane;
 }
+extern "C" int64_t dkd_row_planes_bytes(int32_t Nv, int32_t R, int32_t D) {
+  if (Nv < 0 || R <= 0 || R > 128 || D <= 0 || D % kXKB != 0) return -1;
+  return (int64_t)Nv * (D / kXKB) * 2 * row_pad(R, 0) * 128;
+}
 
-extern "C" int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream) {
-  if (!clips || !planes || Nv < 0) return DKD_ERR_ARG;
-  if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
-  if ((reinterpret_cast<uintptr_t>(clips) | reinterpret_cast<uintptr_t>(planes)) & 15) return DKD_ERR_ALIGN;
+static int pack_rows(const float* x, int32_t Nv, int32_t R, int32_t rpad, int32_t D, float* planes, void* stream) {
+  if (!x || !planes || Nv < 0) return DKD_ERR_ARG;
+  if (R <= 0 || R > rpad || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(planes)) & 15) return DKD_ERR_ALIGN;
   if (Nv == 0) return DKD_OK;
-  pack_clips_tf32_kernel<<<Nv, 256, 0, (cudaStream_t)stream>>>(clips, T, D, planes);
+  pack_rows_tf32_kernel<<<Nv, 256, 0, (cudaStream_t)stream>>>(x, R, rpad, D, planes);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
+}
+extern "C" int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream) {
+  if (T > 32) return DKD_ERR_SHAPE;
+  return pack_rows(clips, Nv, T, 32, D, planes, stream);
+}
+extern "C" int dkd_pack_rows_tf32(const float* xn, int32_t Nv, int32_t R, int32_t D, float* planes, void* stream) {
+  if (R > 128) return DKD_ERR_SHAPE;
+  return pack_rows(xn, Nv, R, row_pad(R, 0), D, planes, stream);
+}
+
+// shared launcher: mode 0 (clip windows) / mode 1 (rows max)
+static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStream_t st) {
+  int dev = 0, sms = 0, max_smem = 0;
+  DKD_CUDA_TRY(cudaGetDevice(&dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int num_kb = D / kXKB;
+  const int ring = D > 448 ? 2 : 3;
+  const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 8192 /* static shared */ + (size_t)kXStageWarps * ring * kXSlotBytes;
+  size_t b_total;
+  if (mode == 0) {
+    const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
+    if ((size_t)max_smem < fixed + b_buf) return DKD_ERR_SHAPE;
+    p.b_bufs = ((size_t)max_smem >= fixed + 2 * b_buf) ? 2 : 1;
+    b_total = (size_t)p.b_bufs * b_buf;
+  } else {
+    p.b_bufs = kXBStages;
+    b_total = (size_t)kXBStages * 2 * p.Npad * 128;
+    if ((size_t)max_smem < fixed + b_total) return DKD_ERR_SHAPE;
+  }
+  const size_t smem = fixed - 8192 + b_total;
+  const int grid = p.Nv < sms ? p.Nv : sms;
+  auto launch = [&](auto kern) -> int {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kXThreads, smem, st>>>(p);
+    return DKD_OK;
+  };
+  int rc;
+  if (mode == 0) {
+    if (ring == 3) rc = (T == 32) ? launch(exact_umma_kernel<0, true, 3>) : launch(exact_umma_kernel<0, false, 3>);
+    else rc = (T == 32) ? launch(exact_umma_kernel<0, true, 2>) : launch(exact_umma_kernel<0, false, 2>);
+  } else {
+    rc = (ring == 3) ? launch(exact_umma_kernel<1, true, 3>) : launch(exact_umma_kernel<1, true, 2>);
+  }
+  if (rc) return rc;
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_score_max_exact(const float* qn, int32_t M, const float* row_planes, int32_t Nv, int32_t R,
+                                   int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg,
+                                   int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list, void* stream) {
+  if (!qn || !row_planes || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
+  if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
+  if (R <= 0 || R > 128 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
+  if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(row_planes)) & 15) return DKD_ERR_ALIGN;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  ExactParams p{};
+  p.q = qn; p.M = M; p.planes = row_planes; p.scale = nullptr;
+  p.Nv = Nv; p.T = 0; p.D = D; p.R = R; p.Npad = row_pad(R, 0); p.mask = mask;
+  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
+  p.vid_ptr = vid_ptr; p.q_list = q_list; p.out_slot = nullptr;
+  return launch_exact(1, p, D, 0, (cudaStream_t)stream);
 }
 
 extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
@@ -455,33 +604,10 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
   if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(clip_planes) | reinterpret_cast<uintptr_t>(prop_scale)) & 15)
     return DKD_ERR_ALIGN;
   if (M == 0 || Nv == 0) return DKD_OK;
-  int dev = 0, sms = 0, max_smem = 0;
-  DKD_CUDA_TRY(cudaGetDevice(&dev));
-  DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int num_kb = D / kXKB;
-  const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
-  const int ring = D > 448 ? 2 : 3;
-  const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 8192 /* static shared */ + (size_t)kXStageWarps * ring * kXSlotBytes;
-  if ((size_t)max_smem < fixed + b_buf) return DKD_ERR_SHAPE;
-  const int b_bufs = ((size_t)max_smem >= fixed + 2 * b_buf) ? 2 : 1;
-  const size_t smem = fixed - 8192 + (size_t)b_bufs * b_buf;
   ExactParams p{};
   p.q = qn; p.M = M; p.planes = clip_planes; p.scale = prop_scale;
-  p.Nv = Nv; p.T = T; p.D = D; p.b_bufs = b_bufs;
+  p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
   p.vid_ptr = vid_ptr; p.q_list = q_list; p.out_slot = out_slot;
-  const int grid = Nv < sms ? Nv : sms;
-  cudaStream_t st = (cudaStream_t)stream;
-  auto launch = [&](auto kern) -> int {
-    DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kXThreads, smem, st>>>(p);
-    return DKD_OK;
-  };
-  int rc;
-  if (ring == 3) rc = (T == 32) ? launch(clip_exact_umma_kernel<true, 3>) : launch(clip_exact_umma_kernel<false, 3>);
-  else rc = (T == 32) ? launch(clip_exact_umma_kernel<true, 2>) : launch(clip_exact_umma_kernel<false, 2>);
-  if (rc) return rc;
-  DKD_LAUNCH_CHECK();
-  return DKD_OK;
+  return launch_exact(0, p, D, T, (cudaStream_t)stream);
 }

@@ -13,7 +13,8 @@ Two precisions
                so the returned top-K (ids, scores) equal the exact path's.
 
 HBM layout per branch (Nv videos, L frames, D features, T clips, P = T(T+1)/2 proposals):
-  frames_n   (Nv, L, D) fp32   L2-normalised frames          frame head, exact
+  frames_n   (Nv, L, D) fp32   L2-normalised frames          frame head, exact (per-frame output)
+  frame_planes (Nv, D/32, 2, L, 32) fp32  tf32 hi/lo planes of frames_n, smem image   frame head, exact + rescoring
   frames_b   (Nv*L, D)  bf16   same, GEMM B operand          frame head, bf16
   clips      (Nv, T, D) fp32   downsampled clips  two-scale, exact + rescoring
   prop_scale (Nv, P)    fp32   1/(w*||mean||)                two-scale, exact + rescoring
@@ -37,6 +38,7 @@ BRANCH_WEIGHTS = (0.7, 0.3)  # inheritance, exploration: method/eval.py:254
 class BranchData:
     frames_n: Optional[torch.Tensor] = None
     frames_b: Optional[torch.Tensor] = None
+    frame_planes: Optional[torch.Tensor] = None
     clips: Optional[torch.Tensor] = None
     clip_planes: Optional[torch.Tensor] = None
     prop_scale: Optional[torch.Tensor] = None
@@ -93,6 +95,8 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
                                         want_bf16="bf16" in precisions)
             bd.frames_n = None if fn is None else fn.view(Nv, L, D)
             bd.frames_b = fb
+            if bd.frames_n is not None and D % 32 == 0:
+                bd.frame_planes = ops.pack_rows(bd.frames_n)
         if "two_scale" in heads:
             if attn_params is None:
                 raise ValueError("two_scale head needs the key/value projections (attn_params)")
@@ -138,12 +142,21 @@ def _branch_weights(nb):
     return BRANCH_WEIGHTS[:nb] if nb == 2 else (1.0,)
 
 
+def _exact_rows(bd: BranchData, qn, pc: PreparedCorpus, csr=None):
+    """Exact max/argmax over the frames: tcgen05 kind::tf32 path when the packed planes exist (D % 32 == 0),
+    the SIMT fp32 kernel otherwise."""
+    if bd.frame_planes is not None:
+        return ops.score_max_exact(qn, bd.frame_planes, pc.L, pc.mask_u8, csr=csr)
+    s, a, _ = ops.score_max_f32(qn, bd.frames_n, pc.mask_u8, csr=csr)
+    return s, a
+
+
 def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", want_arg=False):
     """Per-branch dense (M, Nv) scores of the reference head. Returns list of (scores, argmax)."""
     out = []
     for bd, qn, qb in zip(pc.branches, pq.qn, pq.qb):
         if precision == "exact":
-            s, a, _ = ops.score_max_f32(qn, bd.frames_n, pc.mask_u8)
+            s, a = _exact_rows(bd, qn, pc)
         else:
             s, a = ops.score_max_bf16(qb, pq.M, bd.frames_b, pc.Nv, pc.L, pc.mask_u8)
         out.append((s, a))
@@ -206,7 +219,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     csr = ops.candidates_to_csr(cand, pc.Nv, pc.id_base)
     cand_scores = torch.full((pq.M, Kc), float("-inf"), dtype=torch.float32, device=cand.device)
     if head == "frame":
-        ex = [ops.score_max_f32(qn, bd.frames_n, pc.mask_u8, csr=csr[:2])[0] for bd, qn in zip(pc.branches, pq.qn)]
+        ex = [_exact_rows(bd, qn, pc, csr=csr[:2])[0] for bd, qn in zip(pc.branches, pq.qn)]
         if nb == 2:
             ops.scatter_fuse(ex[0], ex[1], wbs[0], wbs[1], csr, cand_scores)
         else:

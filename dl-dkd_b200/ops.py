@@ -103,6 +103,45 @@ def score_max_f32(qn, xn, mask=None, want_rows=False, csr=None):
     return om, oa, rows
 
 
+def pack_rows(xn):
+    """(Nv, R, D) normalised rows (R <= 128) -> (Nv, D/32, 2, Rpad, 32) fp32: the pre-packed B operand of
+    score_max_exact (tf32 hi / lo planes in the shared-memory layout; once per corpus)."""
+    _chk(xn, torch.float32, "xn")
+    Nv, R, D = xn.shape
+    if D % 32 or R > 128:
+        raise _lib.DkdError("pack_rows: D must be a multiple of 32 and R <= 128")
+    planes = torch.empty((Nv, D // 32, 2, round_up(R, 16), 32), dtype=torch.float32, device=xn.device)
+    _lib.call("dkd_pack_rows_tf32", _p(xn), Nv, R, D, _p(planes), _stream())
+    return planes
+
+
+def score_max_exact(qn, planes, R, mask=None, csr=None):
+    """Exact get_sim_scores core on the tcgen05 kind::tf32 path: qn (M, D) normalised queries, planes =
+    pack_rows(xn) -> (max (M, Nv), first argmax).  csr = (vid_ptr, q_list): listed pairs only, entry order."""
+    _chk(qn, torch.float32, "qn")
+    _chk(planes, torch.float32, "row_planes")
+    M, D = qn.shape
+    Nv = planes.shape[0]
+    if planes.dim() != 5 or planes.shape[1] * 32 != D or planes.shape[3] != round_up(R, 16):
+        raise _lib.DkdError("score_max_exact: row planes do not match (R, D)")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    dev = qn.device
+    if csr is None:
+        om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
+        oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
+        _lib.call("dkd_score_max_exact", _p(qn), M, _p(planes), Nv, R, D, _p(mask), _p(om), _p(oa), Nv, None, None,
+                  _stream())
+    else:
+        vid_ptr, q_list = csr
+        E = q_list.numel()
+        om = torch.empty((E,), dtype=torch.float32, device=dev)
+        oa = torch.empty((E,), dtype=torch.int32, device=dev)
+        _lib.call("dkd_score_max_exact", _p(qn), M, _p(planes), Nv, R, D, _p(mask), _p(om), _p(oa), 0, _p(vid_ptr),
+                  _p(q_list), _stream())
+    return om, oa
+
+
 def pack_clips(clips):
     """(Nv, T, D) clips -> (Nv, D/32, 2, 32, 32) fp32: the pre-packed B operand of the exact clip-scale kernel
     (tf32 hi / lo planes in the shared-memory layout; once per corpus)."""

@@ -89,17 +89,30 @@ int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, i
                       int64_t ld_out, float* out_rows, const int32_t* vid_ptr,
                       const int32_t* q_list, void* stream);
 
-/* Exact (fp32-grade) clip-scale scores through per-clip dot products (SURVEY §7 "linearity") on the
- * tcgen05 tensor cores: kind::tf32 with operands split on the fly (x = hi + lo; lo.hi + hi.lo + hi.hi,
- * fp32 accumulate in TMEM — error inside the summation-order noise of an fp32 einsum):
+/* ---------------------------------------------------------------------------------------
+ * Exact (fp32-grade) scoring on the tcgen05 tensor cores: kind::tf32 with operands split on the fly
+ * (x = hi + lo; lo.hi + hi.lo + hi.hi, fp32 accumulate in TMEM — error inside the summation-order noise of an
+ * fp32 einsum).  The corpus-side operand is pre-packed once per corpus into the shared-memory image of the
+ * MMA's B operand (tf32 hi / lo planes, K-major 128-byte swizzle):
+ *   dkd_pack_rows_tf32  xn (Nv, R, D) normalised rows, R <= 128   -> dkd_row_planes_bytes(Nv, R, D) bytes
+ *   dkd_pack_clips_tf32 clips (Nv, T, D), T <= 32                  -> dkd_clip_planes_bytes(Nv, D) bytes
+ *
+ * dkd_score_max_exact: same results and options as dkd_score_max_f32 (max / first argmax over the R rows of a
+ * video, masked rows exactly -1e10, dense or CSR) without the per-row output; replaces DLDKD.get_sim_scores,
+ * method/model.py:307-329.  D % 32 == 0, D <= 512.
+ *
+ * dkd_clip_score_f32: clip-scale scores through per-clip dot products (SURVEY §7 "linearity"):
  *   d[m, n, i] = qn[m] . clips[n, i];  S[m, n, p(w,s)] = (sum_{i=s}^{s+w-1} d[m,n,i]) * prop_scale[n, p]
  *   out_max = max_p S, out_arg = first argmax_p.  T <= 32, D % 32 == 0, D <= 512, 16-byte aligned rows.
- * clip_planes: the clips pre-packed by dkd_pack_clips_tf32 (once per corpus): per video the shared-memory image
- * of the MMA's B operand (tf32 hi / lo planes, K-major 128-byte swizzle), dkd_clip_planes_bytes(Nv, D) bytes.
- * Same CSR option as dkd_score_max_f32; with out_slot (CSR only) entry e is written to
- * out_max[out_slot[e]] / out_arg[out_slot[e]] (scatter into a dense matrix) instead of out_max[e].
+ * Same CSR option; with out_slot (CSR only) entry e is written to out_max[out_slot[e]] / out_arg[out_slot[e]]
+ * (scatter into a dense matrix) instead of out_max[e].
  * Replaces get_clip_scale_scores of the two-scale head, fp32 reference flavour.
  */
+int64_t dkd_row_planes_bytes(int32_t Nv, int32_t R, int32_t D);
+int dkd_pack_rows_tf32(const float* xn, int32_t Nv, int32_t R, int32_t D, float* planes, void* stream);
+int dkd_score_max_exact(const float* qn, int32_t M, const float* row_planes, int32_t Nv, int32_t R,
+                        int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg, int64_t ld_out,
+                        const int32_t* vid_ptr, const int32_t* q_list, void* stream);
 int64_t dkd_clip_planes_bytes(int32_t Nv, int32_t D);
 int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream);
 int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,

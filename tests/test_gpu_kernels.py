@@ -111,6 +111,40 @@ def test_score_max_f32_no_mask_and_fully_masked_video(ops):
     assert (om2.cpu() - s_ref2).abs().max() <= FP32_TOL
 
 
+@pytest.mark.parametrize("M,Nv,L,D", [(50, 23, 128, 384), (300, 9, 77, 64), (1, 3, 16, 512), (260, 40, 128, 384),
+                                      (129, 5, 100, 128)])
+def test_score_max_exact_matches_get_sim_scores(ops, M, Nv, L, D):
+    """The tcgen05 kind::tf32 exact path (split operands, packed row planes) vs the oracle's get_sim_scores:
+    ragged masks, R not a multiple of 16, a fully masked video, several tiles per video; CSR == dense."""
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=40 + M)
+    mask = mask.clone()
+    if Nv > 2:
+        mask[2] = 0
+    q = synth.encoded_queries(M, D, seed=50 + M)
+    s_ref, rows_ref, a_ref = O.get_sim_scores(q, frames, mask)
+    qc, fc, mc = _cuda(q, frames, mask.to(torch.uint8))
+    qn, _ = ops.normalize_rows(qc)
+    xn, _ = ops.normalize_rows(fc)
+    planes = ops.pack_rows(xn.view(Nv, L, D))
+    om, oa = ops.score_max_exact(qn, planes, L, mc)
+    torch.cuda.synchronize()
+    assert (om.cpu() - s_ref).abs().max() <= FP32_TOL
+    if Nv > 2:
+        assert torch.equal(om[:, 2].cpu(), torch.full((M,), -1e10)) and (oa[:, 2] == 0).all()
+    ok, nbad = _argmax_ok(oa.cpu(), rows_ref, a_ref, FP32_TOL)
+    assert ok, f"{nbad} argmax mismatches beyond fp32 ties"
+    om2, _ = ops.score_max_exact(qn, planes, L, None)
+    assert (om2.cpu() - O.get_sim_scores(q, frames, None)[0]).abs().max() <= FP32_TOL
+    # CSR restriction reproduces the dense bits
+    g = torch.Generator().manual_seed(60)
+    gap = torch.rand(M, Nv, generator=g)
+    vid_ptr, q_list, slot = ops.select_pairs_csr(gap.cuda(), 0.4)
+    n_e = int(vid_ptr[-1].item())
+    cs, ck = ops.score_max_exact(qn, planes, L, mc, csr=(vid_ptr, q_list))
+    sl = slot[:n_e].long()
+    assert torch.equal(cs[:n_e], om.flatten()[sl]) and torch.equal(ck[:n_e], oa.flatten()[sl])
+
+
 @pytest.mark.parametrize("M,Nv,D,T", [(70, 11, 384, 32), (5, 3, 64, 32), (300, 160, 384, 32), (133, 7, 128, 8),
                                       (260, 5, 512, 32)])
 def test_clip_score_f32(ops, M, Nv, D, T):

@@ -1,0 +1,90 @@
+"""Full-size runs of BASELINE.json's eval configs (synthetic features of the named shapes, random-init DL-DKD++
+encoders) through size-independent properties:
+
+  * the tcgen05 path + exact rescoring returns the same top-100 (ids AND scores) as the all-exact path,
+    for EVERY query of the config;
+  * R@K computed from the ranked top-100 equals R@K computed from the rank of the ground-truth video in the
+    dense exact fused scores (eval_q2m route);
+  * video-sharded ranking + merge equals the unsharded ranking.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {
+    # BASELINE.json configs[0..2]
+    "charades": dict(Nv=1334, L=128, Dv=1024, Nq=3720, Lq=30, Dq=768, H=384, T=32),
+    "tvr": dict(Nv=2179, L=128, Dv=3072, Nq=10895, Lq=30, Dq=768, H=384, T=32),
+    "activitynet": dict(Nv=4885, L=128, Dv=1024, Nq=17031, Lq=30, Dq=1024, H=384, T=32),
+}
+
+
+def _setup(name, head):
+    import bench
+    from dkd_b200 import engine
+    from dkd_b200.model import DLDKD
+    dev = torch.device("cuda")
+    shape = SHAPES[name]
+    model, frames, mask, qs = bench.synth_encoded(shape, dev, 0, DLDKD)
+    if name == "charades":  # ragged corpus for one of the configs: lengths 64..128, padding zeroed like cat_tensor
+        g = torch.Generator(device=dev).manual_seed(77)
+        lengths = torch.randint(64, shape["L"] + 1, (shape["Nv"],), device=dev, generator=g)
+        mask = (torch.arange(shape["L"], device=dev)[None] < lengths[:, None]).float()
+        frames = [f * mask[:, :, None] for f in frames]
+    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                               T=shape["T"], heads=(head,))
+    pq = engine.prepare_queries([q.contiguous() for q in qs])
+    return shape, engine, pc, pq, frames, mask, model
+
+
+@pytest.mark.parametrize("name,head", [("charades", "two_scale"), ("charades", "frame"), ("tvr", "two_scale"),
+                                       ("tvr", "frame"), ("activitynet", "two_scale")])
+def test_config_bf16_rank_equals_exact_rank(ops, name, head):
+    shape, engine, pc, pq, *_ = _setup(name, head)
+    K = 100
+    s_ex, i_ex = engine.rank(pc, pq, K=K, head=head, precision="exact")
+    s_bf, i_bf = engine.rank(pc, pq, K=K, head=head, precision="bf16", rescore=True, Kc=128)
+    torch.cuda.synchronize()
+    same_ids = (i_bf == i_ex).all(dim=1)
+    assert bool(same_ids.all()), f"{name}/{head}: {int((~same_ids).sum())} of {pq.M} queries differ in their top-{K}"
+    assert torch.equal(s_bf, s_ex)
+    # ranked lists are sorted (score desc, id asc on ties) and ids are valid and unique
+    assert bool((s_ex[:, :-1] >= s_ex[:, 1:]).all())
+    assert int(i_ex.min()) >= 0 and int(i_ex.max()) < shape["Nv"]
+    assert bool((torch.sort(i_ex, dim=1).values[:, 1:] != torch.sort(i_ex, dim=1).values[:, :-1]).all())
+
+
+def test_config_recall_from_topk_equals_recall_from_gt_rank(ops):
+    """R@1/5/10/100 two ways on the TVR-shaped config: ranked top-100 lists vs rank of the GT video (eval_q2m)."""
+    from dkd_b200 import eval as E
+    shape, engine, pc, pq, *_ = _setup("tvr", "two_scale")
+    Nq, Nv = shape["Nq"], shape["Nv"]
+    t2v = {q: [q % Nv] for q in range(Nq)}                      # caption ids vid{q mod Nv}#enc#{q div Nv}
+    _, top = engine.rank(pc, pq, K=100, head="two_scale", precision="bf16")
+    fused, _ = engine.score_two_scale_head(pc, pq, "exact")
+    ptr = torch.arange(Nq + 1, dtype=torch.int32, device="cuda")
+    gts = (torch.arange(Nq, device="cuda") % Nv).to(torch.int32)
+    ranks = ops.rank_of_gt(fused, ptr, gts).cpu().numpy()
+    from_rank = [100.0 * np.count_nonzero(ranks <= k) / Nq for k in (1, 5, 10, 100)]
+    from_topk = E.recall_from_topk(top, t2v)
+    assert np.allclose(from_rank, from_topk), (from_rank, from_topk)
+
+
+def test_config_sharded_rank_equals_unsharded(ops):
+    """Charades-shaped corpus split over 4 video shards (the 4-GPU algebra on one device): local bf16 rank with
+    global ids + dkd_merge_topk == the unsharded rank."""
+    shape, engine, pc, pq, frames, mask, model = _setup("charades", "two_scale")
+    params = [tuple(t.detach() for t in p) for p in model.attention_params()]
+    s_all, i_all = engine.rank(pc, pq, K=100, head="two_scale", precision="bf16")
+    ls, li = [], []
+    for r in range(4):
+        lo, hi = engine.shard_range(shape["Nv"], r, 4)
+        pcs = engine.prepare_corpus([f[lo:hi].contiguous() for f in frames], mask[lo:hi].contiguous(), params,
+                                    T=shape["T"], heads=("two_scale",), id_base=lo)
+        s, i = engine.rank(pcs, pq, K=100, head="two_scale", precision="bf16")
+        ls.append(s)
+        li.append(i)
+    ms, mi = ops.merge_topk(torch.stack(ls), torch.stack(li))
+    assert torch.equal(mi, i_all) and torch.equal(ms, s_all)

@@ -133,40 +133,49 @@ def synth_encoded(shape, device, shard_seed, dkd_model_cls):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cpu_baseline(shape, workload, sample_queries, threads=None):
+class CpuBaseline:
     """The oracle port of the reference's CPU eval loop on a bounded sample of the same workload:
-    `sample_queries` queries x the full corpus, all host threads.  Returns dict for the JSON line."""
-    from oracle import oracle as O
-    from dkd_b200.model import DLDKD
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    dev = torch.device("cpu")
-    sub = dict(shape)
-    sub["Nq"] = sample_queries
-    t_setup = time.perf_counter()
-    model, frames, mask, qs = synth_encoded(sub, dev, 0, DLDKD)
-    with torch.no_grad():
+    `sample_queries` queries x the full corpus, all host threads.  Setup (synthetic features, random-init
+    encoders, corpus-side preparation) happens once in the constructor and is not timed."""
+
+    def __init__(self, shape, workload, max_queries, threads=None):
+        from oracle import oracle as O
+        from dkd_b200.model import DLDKD
+        self.O, self.shape, self.workload = O, shape, workload
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        sub = dict(shape)
+        sub["Nq"] = max_queries
+        model, self.frames, self.mask, self.qs = synth_encoded(sub, torch.device("cpu"), 0, DLDKD)
         if workload == "tvr_two_scale":
-            lengths = mask.sum(1).long()
-            props, keys, vals = [], [], []
-            for f, (kw, kb, vw, vb) in zip(frames, model.attention_params()):
-                props.append(O.build_proposals(O.downsample_clips(f, lengths, shape["T"])))
-                keys.append(torch.nn.functional.linear(f, kw, kb))
-                vals.append(torch.nn.functional.linear(f, vw, vb))
-            t_setup = time.perf_counter() - t_setup
+            with torch.no_grad():
+                lengths = self.mask.sum(1).long()
+                self.props, self.keys, self.vals = [], [], []
+                for f, (kw, kb, vw, vb) in zip(self.frames, model.attention_params()):
+                    self.props.append(O.build_proposals(O.downsample_clips(f, lengths, shape["T"])))
+                    self.keys.append(torch.nn.functional.linear(f, kw, kb))
+                    self.vals.append(torch.nn.functional.linear(f, vw, vb))
+
+    def run(self, sample_queries):
+        """One timed pass -> dict for the JSON line."""
+        O = self.O
+        qs = [q[:sample_queries] for q in self.qs]
+        with torch.no_grad():
             t0 = time.perf_counter()
-            O.cpu_eval_two_scale(qs, props, keys, vals, mask, bsz=50, K=K_TOP)
+            if self.workload == "tvr_two_scale":
+                O.cpu_eval_two_scale(qs, self.props, self.keys, self.vals, self.mask, bsz=50, K=K_TOP)
+            else:
+                O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
             dt = time.perf_counter() - t0
-        else:
-            t_setup = time.perf_counter() - t_setup
-            t0 = time.perf_counter()
-            O.cpu_eval_frame_head(qs, frames, mask, bsz=50, K=K_TOP)
-            dt = time.perf_counter() - t0
-    pairs = sample_queries * shape["Nv"]
-    return {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_queries} queries x {shape['Nv']} videos ({workload}, oracle/oracle.py "
-                      f"cpu_eval loop, batches of 50, torch {torch.__version__} CPU, {dt:.1f} s)",
-            "seconds": dt}
+        pairs = sample_queries * self.shape["Nv"]
+        return {"value": pairs / dt, "unit": "pairs/s", "cores": self.threads, "kind": "port",
+                "sample": f"{sample_queries} queries x {self.shape['Nv']} videos ({self.workload}, oracle/oracle.py "
+                          f"cpu_eval loop, batches of 50, torch {torch.__version__} CPU, {dt:.1f} s)",
+                "seconds": dt}
+
+
+def run_cpu_baseline(shape, workload, sample_queries, threads=None):
+    return CpuBaseline(shape, workload, sample_queries, threads).run(sample_queries)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,12 +210,16 @@ def main():
         if rank != 0:
             return
         nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
-        vals = []
-        for _ in range(max(args.warmup, 0)):
-            run_cpu_baseline(shape, args.workload, 50)
-        last = None
+        cpu = CpuBaseline(shape, args.workload, nq)
+        first = cpu.run(50)                                     # untimed: also sizes the sample
+        for _ in range(max(args.warmup - 1, 0)):
+            cpu.run(50)
+        # keep the whole run within a few minutes: K steps x sample <= ~200 s of CPU work
+        budget_q = int(first["value"] * (200.0 / max(args.steps, 1)) / shape["Nv"]) // 50 * 50
+        nq = max(50, min(nq, budget_q))
+        vals, last = [], None
         for _ in range(max(args.steps, 1)):
-            last = run_cpu_baseline(shape, args.workload, nq)
+            last = cpu.run(nq)
             vals.append(last["value"])
         v = float(np.mean(vals))
         sec = float(np.mean([nq * shape["Nv"] / x for x in vals]))

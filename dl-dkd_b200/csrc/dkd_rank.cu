@@ -28,20 +28,40 @@ __device__ __forceinline__ void warp_bitonic_desc(u64* a, int S, int lane) {
   }
 }
 
-// Streaming top-K by one warp: `list` = first K slots (sorted desc), queue = slots [K, S).
+// Bitonic merge (descending) of a bitonic sequence of S keys by one warp.
+__device__ __forceinline__ void warp_bitonic_merge_desc(u64* a, int S, int lane) {
+  for (int j = S >> 1; j > 0; j >>= 1) {
+    for (int t = lane; t < (S >> 1); t += 32) {
+      const int i = ((t / j) * (j << 1)) + (t % j);
+      const u64 x = a[i], y = a[i + j];
+      if (x < y) { a[i] = y; a[i + j] = x; }
+    }
+    __syncwarp();
+  }
+}
+
+// Streaming top-K by one warp: `list` = first H = S/2 slots (sorted desc, K <= H), queue = slots [H, S).
+// flush: sort the queue alone, then keep the H best of (list, queue) with one compare-exchange pass against the
+// reversed queue (the result is bitonic) and a bitonic merge — half the compare-exchanges of sorting all S slots.
 struct WarpSelect {
   u64* buf;   // S slots
-  int S, K, lane;
+  int S, H, K, lane;
   int qn;     // queued (warp-uniform)
   u64 thresh; // K-th best so far (warp-uniform)
   __device__ void init(u64* b, int S_, int K_, int lane_) {
-    buf = b; S = S_; K = K_; lane = lane_; qn = 0; thresh = 0ull;
+    buf = b; S = S_; H = S_ >> 1; K = K_; lane = lane_; qn = 0; thresh = 0ull;
     for (int i = lane; i < S; i += 32) buf[i] = 0ull;
     __syncwarp();
   }
   __device__ void flush() {
-    warp_bitonic_desc(buf, S, lane);
-    for (int i = K + lane; i < S; i += 32) buf[i] = 0ull;
+    warp_bitonic_desc(buf + H, H, lane);                 // queue, descending (empty slots are 0: they sink)
+    for (int i = lane; i < H; i += 32) {                 // list[i] vs queue[H-1-i]: the H largest, bitonic
+      const u64 x = buf[i], y = buf[S - 1 - i];
+      if (y > x) buf[i] = y;
+    }
+    __syncwarp();
+    warp_bitonic_merge_desc(buf, H, lane);
+    for (int i = H + lane; i < S; i += 32) buf[i] = 0ull;
     __syncwarp();
     thresh = buf[K - 1];
     qn = 0;
@@ -51,10 +71,10 @@ struct WarpSelect {
     const bool take = valid && key > thresh;
     const unsigned bal = __ballot_sync(0xffffffffu, take);
     if (bal == 0u) return;
-    if (take) buf[K + qn + __popc(bal & ((1u << lane) - 1u))] = key;
+    if (take) buf[H + qn + __popc(bal & ((1u << lane) - 1u))] = key;
     qn += __popc(bal);
     __syncwarp();
-    if (K + qn + 32 > S) flush();
+    if (qn + 32 > H) flush();
   }
 };
 

@@ -27,8 +27,9 @@ PROTOTYPES = {
     "dkd_score_max_exact": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P],
     "dkd_clip_planes_bytes": [_I, _I],
     "dkd_pack_clips_tf32": [_P, _I, _I, _I, _P, _P],
-    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P],
-    "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P],
+    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P],
+    "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _F, _P],
+    "dkd_select_flagged": [_P, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P],
     "dkd_select_pairs_csr": [_P, _I, _I, _L, _F, _L, _P, _P, _P, _P, _P],
     "dkd_key_clip_dots": [_P, _P, _I, _I, _I, _I, _P, _P],
     "dkd_frame_attn_table": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -76,7 +77,7 @@ def check(code: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3}
+KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3}  # (memsets are not counted)
 _launches = 0
 _timed_names = set()
 _timed_events = {}

@@ -52,7 +52,7 @@ struct ExactParams {
   int R, Npad;                 // rows mode: rows per video, padded to a multiple of 16 (UMMA N)
   const uint8_t* mask;         // rows mode: (Nv, R) or null
   float* out_max; int32_t* out_arg; int64_t ld_out;
-  const int32_t* vid_ptr; const int32_t* q_list; const int32_t* out_slot;
+  const int32_t* vid_ptr; const int32_t* vid_cnt; const int32_t* q_list; const int32_t* out_slot;
 };
 
 struct __align__(8) ExactCtl {
@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 }
 
 __device__ __forceinline__ void video_range(const ExactParams& p, int n, int& e0, int& count) {
-  if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_ptr[n + 1] - e0; }
+  if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_cnt ? p.vid_cnt[n] : p.vid_ptr[n + 1] - e0; }
   else { e0 = 0; count = p.M; }
 }
 
@@ -588,17 +588,17 @@ extern "C" int dkd_score_max_exact(const float* qn, int32_t M, const float* row_
   p.q = qn; p.M = M; p.planes = row_planes; p.scale = nullptr;
   p.Nv = Nv; p.T = 0; p.D = D; p.R = R; p.Npad = row_pad(R, 0); p.mask = mask;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
-  p.vid_ptr = vid_ptr; p.q_list = q_list; p.out_slot = nullptr;
+  p.vid_ptr = vid_ptr; p.vid_cnt = nullptr; p.q_list = q_list; p.out_slot = nullptr;
   return launch_exact(1, p, D, 0, (cudaStream_t)stream);
 }
 
 extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
                                   int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
-                                  int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
-                                  const int32_t* out_slot, void* stream) {
+                                  int64_t ld_out, const int32_t* vid_ptr, const int32_t* vid_cnt,
+                                  const int32_t* q_list, const int32_t* out_slot, void* stream) {
   if (!qn || !clip_planes || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
   if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
-  if (out_slot && !vid_ptr) return DKD_ERR_ARG;
+  if ((out_slot || vid_cnt) && !vid_ptr) return DKD_ERR_ARG;
   if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
   if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(clip_planes) | reinterpret_cast<uintptr_t>(prop_scale)) & 15)
@@ -608,6 +608,6 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
   p.q = qn; p.M = M; p.planes = clip_planes; p.scale = prop_scale;
   p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
-  p.vid_ptr = vid_ptr; p.q_list = q_list; p.out_slot = out_slot;
+  p.vid_ptr = vid_ptr; p.vid_cnt = vid_cnt; p.q_list = q_list; p.out_slot = out_slot;
   return launch_exact(0, p, D, T, (cudaStream_t)stream);
 }

@@ -247,6 +247,40 @@ __global__ void pair_fill_kernel(const float* __restrict__ gap, int M, int Nv, i
     }
   }
 }
+// ---- flagged-pair lists from the GEMM's bit matrix: one block per 32 videos (one word column) ----------------
+// flags (M, W) uint32, bit (n & 31) of word [m][n >> 5].  Per video a contiguous run of q_list / slot entries
+// (any order inside the run), runs placed by a global cursor: vid_begin[n], vid_cnt[n].
+__global__ void __launch_bounds__(256)
+flag_select_kernel(const uint32_t* __restrict__ flags, int M, int Nv, int W, int64_t ld, int32_t* __restrict__ cursor,
+                   int32_t* __restrict__ vid_begin, int32_t* __restrict__ vid_cnt, int32_t* __restrict__ q_list,
+                   int32_t* __restrict__ slot, int64_t cap) {
+  __shared__ int cnt[32], base[32], cur[32];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (tid < 32) { cnt[tid] = 0; cur[tid] = 0; }
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) {
+    uint32_t w = flags[(int64_t)m * W + g];
+    while (w) { const int b = __ffs(w) - 1; w &= w - 1; atomicAdd(&cnt[b], 1); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int b = 0; b < 32; ++b) { base[b] = tot; tot += cnt[b]; }
+    const int start = atomicAdd(cursor, tot);
+    for (int b = 0; b < 32; ++b) base[b] += start;
+  }
+  __syncthreads();
+  if (tid < 32 && g * 32 + tid < Nv) { vid_begin[g * 32 + tid] = base[tid]; vid_cnt[g * 32 + tid] = cnt[tid]; }
+  for (int m = tid; m < M; m += 256) {
+    uint32_t w = flags[(int64_t)m * W + g];
+    while (w) {
+      const int b = __ffs(w) - 1; w &= w - 1;
+      const int64_t e = (int64_t)base[b] + atomicAdd(&cur[b], 1);
+      if (e < cap) { q_list[e] = m; slot[e] = (int)((int64_t)m * ld + g * 32 + b); }
+    }
+  }
+}
+
 // out[slot[e]] = fl(wa * a[e]) + fl(wb * b[e])  (b may be null: out[slot[e]] = a[e])
 __global__ void scatter_fuse_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
                                     const int32_t* __restrict__ slot, const int32_t* __restrict__ total_ptr,
@@ -364,6 +398,20 @@ extern "C" int dkd_select_pairs_csr(const float* gap, int32_t M, int32_t Nv, int
   cand_scan_kernel<<<1, 1024, 0, st>>>(counts, Nv, vid_ptr);
   DKD_LAUNCH_CHECK();
   pair_fill_kernel<<<blocks, 256, 0, st>>>(gap, M, Nv, ld, tau, counts, vid_ptr, q_list, slot, cap);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_select_flagged(const uint32_t* flags, int32_t M, int32_t Nv, int64_t ld, int64_t cap,
+                                  int32_t* cursor, int32_t* vid_begin, int32_t* vid_cnt, int32_t* q_list,
+                                  int32_t* slot, void* stream) {
+  if (!flags || !cursor || !vid_begin || !vid_cnt || !q_list || !slot || M < 0 || Nv <= 0 || ld < Nv || cap < 0)
+    return DKD_ERR_ARG;
+  if ((int64_t)M * ld > 0x7fffffffLL) return DKD_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  DKD_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(int32_t), st));
+  const int W = (Nv + 31) / 32;
+  flag_select_kernel<<<W, 256, 0, st>>>(flags, M, Nv, W, ld, cursor, vid_begin, vid_cnt, q_list, slot, cap);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -16,7 +16,7 @@
 //             of one video; the column position rides in the 4 low mantissa bits of the score
 //             (LOP3 + 3 FMNMX per element), the 16-column chunk id is tracked once per chunk.
 //             Halves are merged through shared memory; direct fp32 / int32 stores of
-//             (max, first argmax, gap to the runner-up).
+//             (max, first argmax, gap to the runner-up) and/or one bit per pair "gap below tau".
 // A work item = (query tile of 128, chunk of kVideoChunk videos); items are ordered query-tile
 // fastest so that CTAs running at the same time stream the same corpus rows out of L2.
 //
@@ -79,6 +79,9 @@ struct GemmParams {
   float* out_max;
   int32_t* out_arg;
   float* out_gap;     // optional: best - runner-up (bf16-level ambiguity of the argmax)
+  uint32_t* out_flags; // optional: bit (n & 31) of word [m][n >> 5] set when that gap is below `tau`
+  float tau;
+  int flag_words;     // words per query row = ceil(Nv / 32)
   int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0,
                       // 4 = MMA does not wait for the corpus ring, 8 = no corpus TMA at all (timing experiments)
   int64_t ld_out;
@@ -345,7 +348,9 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const int64_t o64 = (int64_t)m * p.ld_out + v;
             p.out_max[o64] = val;
             if (p.out_arg) p.out_arg[o64] = idx;
-            if (p.out_gap) p.out_gap[o64] = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
+            const float gap = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
+            if (p.out_gap) p.out_gap[o64] = gap;
+            if (p.out_flags && gap < p.tau) atomicOr(&p.out_flags[(int64_t)m * p.flag_words + (v >> 5)], 1u << (v & 31));
           }
         }
       }
@@ -427,7 +432,8 @@ static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const
 
 extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                                   int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
-                                  int32_t* out_arg, float* out_gap, int64_t ld_out, void* stream) {
+                                  int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
+                                  float tau, void* stream) {
   if (!q_bf16 || !x_bf16 || !out_max || M < 0 || Nv < 0 || ld_out < Nv) return DKD_ERR_ARG;
   if (Mpad < M || Mpad % kBlockM != 0) return DKD_ERR_SHAPE;
   if (R <= 0 || R > 4096 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
@@ -473,6 +479,7 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
   p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
   { const char* e = getenv("DKD_GEMM_DEBUG"); p.debug_flags = e ? atoi(e) : 0; }
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
+  p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
   // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
   const int num_q_tiles = Mpad / (kBlockM * cta);
   const int workers = sms / cta;

@@ -170,8 +170,8 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
                          want_frame=False, tau=AMBIGUITY_TAU):
     """Returns (fused (M, Nv), per-branch list of dict(clip, key_clip, frame|None)).
 
-    precision="bf16": the tcgen05 GEMM also reports, per (query, video), the gap between the best and
-    the runner-up proposal.  The key clip steers the frame-scale term discontinuously, so pairs whose
+    precision="bf16": the tcgen05 GEMM also flags (one bit per pair) the (query, video) pairs whose gap between
+    the best and the runner-up proposal is small.  The key clip steers the frame-scale term discontinuously, so pairs whose
     gap is below `tau` (the bf16 noise floor on score differences) get their clip score and key clip
     recomputed by the exact kernel before the frame-scale gather; tau=0 disables the pass."""
     nb = len(pc.branches)
@@ -184,9 +184,9 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
             q, tab = qn, bd.table_f
         else:
             if tau > 0:
-                s_clip, k_clip, gap = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P, want_gap=True)
-                csr = ops.select_pairs_csr(gap, tau)
-                ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2], scatter=(csr[2], s_clip, k_clip))
+                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P, flag_tau=tau)
+                vb, ql, vc, slot = ops.select_flagged(flags, pc.Nv)
+                ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=(vb, ql, vc), scatter=(slot, s_clip, k_clip))
             else:
                 s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
             q, tab = qh, bd.table_h

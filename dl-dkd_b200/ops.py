@@ -157,8 +157,9 @@ def pack_clips(clips):
 def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
     """Exact clip-scale max/argmax over the P proposals via per-clip dots on the tcgen05
     kind::tf32 path.  qn (M, D) normalised queries; clips: (Nv, T, D) fp32 or its pack_clips() form (5-D).
-    csr = (vid_ptr, q_list): only the listed (query, video) pairs, results in entry order; with
-    scatter = (slot, out_max, out_arg) entry e is written into the dense matrices at slot[e] instead."""
+    csr = (vid_ptr, q_list) [CSR by video] or (vid_begin, q_list, vid_cnt) [select_flagged runs]: only the listed
+    (query, video) pairs, results in entry order; with scatter = (slot, out_max, out_arg) entry e is written
+    into the dense matrices at slot[e] instead."""
     _chk(qn, torch.float32, "qn")
     _chk(prop_scale, torch.float32, "prop_scale")
     planes = clips if clips.dim() == 5 else pack_clips(clips)
@@ -173,9 +174,10 @@ def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
         om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
         oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
         _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), Nv,
-                  None, None, None, _stream())
+                  None, None, None, None, _stream())
         return om, oa
-    vid_ptr, q_list = csr
+    vid_ptr, q_list = csr[0], csr[1]
+    vid_cnt = csr[2] if len(csr) > 2 else None
     if scatter is not None:
         slot, om, oa = scatter
         _chk(om, torch.float32, "out_max")
@@ -186,13 +188,14 @@ def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
         om = torch.empty((E,), dtype=torch.float32, device=dev)
         oa = torch.empty((E,), dtype=torch.int32, device=dev)
     _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), 0,
-              _p(vid_ptr), _p(q_list), _p(slot), _stream())
+              _p(vid_ptr), _p(vid_cnt), _p(q_list), _p(slot), _stream())
     return om, oa
 
 
-def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None, want_gap=False):
+def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None, want_gap=False, flag_tau=None):
     """tcgen05 GEMM + fused max/argmax: q_bf16 (Mpad,D), x_bf16 (Nv*R, D) -> (max (M,Nv), argmax (M,Nv))
-    [+ gap (M,Nv) = best - runner-up when want_gap]."""
+    [+ gap (M,Nv) = best - runner-up when want_gap] [+ flags (M, ceil(Nv/32)) uint32 bit matrix of the pairs
+    whose gap is below flag_tau]."""
     _chk(q_bf16, torch.bfloat16, "q_bf16")
     _chk(x_bf16, torch.bfloat16, "x_bf16")
     Mpad, D = q_bf16.shape
@@ -204,9 +207,32 @@ def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=No
     om = out_max if out_max is not None else torch.empty((M, Nv), dtype=torch.float32, device=dev)
     oa = out_arg if out_arg is not None else torch.empty((M, Nv), dtype=torch.int32, device=dev)
     og = torch.empty((M, Nv), dtype=torch.float32, device=dev) if want_gap else None
+    fl = torch.zeros((M, (Nv + 31) // 32), dtype=torch.int32, device=dev) if flag_tau is not None else None
     _lib.call("dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D, _p(mask), _p(om), _p(oa), _p(og), Nv,
-              _stream())
-    return (om, oa, og) if want_gap else (om, oa)
+              _p(fl), float(flag_tau or 0.0), _stream())
+    out = (om, oa)
+    if want_gap:
+        out += (og,)
+    if flag_tau is not None:
+        out += (fl,)
+    return out
+
+
+def select_flagged(flags, Nv, cap=None):
+    """Bit matrix of flagged pairs (score_max_bf16 flag_tau) -> (vid_begin, q_list, vid_cnt, slot): per-video
+    runs of query indices / dense slots m * Nv + n."""
+    _chk(flags, torch.int32, "flags")
+    M = flags.shape[0]
+    cap = M * Nv if cap is None else cap
+    dev = flags.device
+    cursor = torch.empty((1,), dtype=torch.int32, device=dev)
+    vid_begin = torch.empty((Nv,), dtype=torch.int32, device=dev)
+    vid_cnt = torch.empty((Nv,), dtype=torch.int32, device=dev)
+    q_list = torch.empty((cap,), dtype=torch.int32, device=dev)
+    slot = torch.empty((cap,), dtype=torch.int32, device=dev)
+    _lib.call("dkd_select_flagged", _p(flags), M, Nv, Nv, cap, _p(cursor), _p(vid_begin), _p(vid_cnt), _p(q_list),
+              _p(slot), _stream())
+    return vid_begin, q_list, vid_cnt, slot
 
 
 def select_pairs_csr(gap, tau, cap=None):

@@ -104,8 +104,9 @@ int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, i
  * dkd_clip_score_f32: clip-scale scores through per-clip dot products (SURVEY §7 "linearity"):
  *   d[m, n, i] = qn[m] . clips[n, i];  S[m, n, p(w,s)] = (sum_{i=s}^{s+w-1} d[m,n,i]) * prop_scale[n, p]
  *   out_max = max_p S, out_arg = first argmax_p.  T <= 32, D % 32 == 0, D <= 512, 16-byte aligned rows.
- * Same CSR option; with out_slot (CSR only) entry e is written to out_max[out_slot[e]] / out_arg[out_slot[e]]
- * (scatter into a dense matrix) instead of out_max[e].
+ * Same CSR option (vid_cnt, optional: video n owns vid_cnt[n] entries from vid_ptr[n] instead of the CSR run
+ * vid_ptr[n] .. vid_ptr[n+1]); with out_slot (list form only) entry e is written to out_max[out_slot[e]] /
+ * out_arg[out_slot[e]] (scatter into a dense matrix) instead of out_max[e].
  * Replaces get_clip_scale_scores of the two-scale head, fp32 reference flavour.
  */
 int64_t dkd_row_planes_bytes(int32_t Nv, int32_t R, int32_t D);
@@ -117,8 +118,8 @@ int64_t dkd_clip_planes_bytes(int32_t Nv, int32_t D);
 int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, float* planes, void* stream);
 int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
                        int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
-                       int64_t ld_out, const int32_t* vid_ptr, const int32_t* q_list,
-                       const int32_t* out_slot, void* stream);
+                       int64_t ld_out, const int32_t* vid_ptr, const int32_t* vid_cnt,
+                       const int32_t* q_list, const int32_t* out_slot, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * bf16 tcgen05/TMEM scoring GEMM with fused max/argmax epilogue (the hot kernel).
@@ -133,10 +134,19 @@ int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, con
  * gap is below the bf16 noise floor have an ambiguous argmax and are re-resolved in fp32
  * (dkd_select_pairs_csr -> dkd_clip_score_f32 (CSR, out_slot)).  Scores carry the column
  * position in their 4 low mantissa bits inside the kernel: returned values are exact to 8 ulp.
+ * out_flags (optional, caller-zeroed, (M, ceil(Nv/32)) uint32): bit (n & 31) of word [m][n >> 5] is set when
+ * that gap is below tau — the compact form consumed by dkd_select_flagged (no dense gap round trip).
  */
 int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                        int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
-                       int32_t* out_arg, float* out_gap, int64_t ld_out, void* stream);
+                       int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags, float tau,
+                       void* stream);
+
+/* Per-video lists of the flagged pairs of a dkd_score_max_bf16 bit matrix: video n owns entries
+ * [vid_begin[n], vid_begin[n] + vid_cnt[n]) of q_list (query index) / slot (m * ld + n), in any order; runs
+ * are placed by a global cursor (1 int scratch).  One pass over the bit matrix, one block per 32 videos. */
+int dkd_select_flagged(const uint32_t* flags, int32_t M, int32_t Nv, int64_t ld, int64_t cap, int32_t* cursor,
+                       int32_t* vid_begin, int32_t* vid_cnt, int32_t* q_list, int32_t* slot, void* stream);
 
 /* Ambiguous-pair bookkeeping: CSR (by video) of all pairs (m, n) with gap[m, n] < tau.
  * counts (Nv) scratch; vid_ptr (Nv+1); q_list / slot (cap entries; slot = m * ld + n).  Entries beyond

@@ -192,6 +192,12 @@ def test_clip_score_f32_csr_and_scatter(ops):
     sel = (gap < 0.3).cuda()
     assert torch.equal(out_m[sel], dm[sel]) and torch.equal(out_a[sel], da[sel])
     assert (out_m[~sel] == -7.0).all() and (out_a[~sel] == -7).all()
+    # (begin, count) runs instead of a CSR: same entries, explicit counts
+    counts = (vid_ptr[1:] - vid_ptr[:-1]).contiguous()
+    out_m2 = torch.full((M, Nv), -7.0, device="cuda")
+    out_a2 = torch.full((M, Nv), -7, dtype=torch.int32, device="cuda")
+    ops.clip_score_f32(qn, clips, ps, csr=(vid_ptr[:-1].contiguous(), q_list, counts), scatter=(slot, out_m2, out_a2))
+    assert torch.equal(out_m2, out_m) and torch.equal(out_a2, out_a)
 
 
 @pytest.mark.parametrize("M,pad,Nv,R,D,masked", [
@@ -216,8 +222,19 @@ def test_score_max_bf16(ops, M, pad, Nv, R, D, masked):
     _, qb = ops.normalize_rows(qc, want_f32=False, want_bf16=True, rows_pad=Mpad)
     _, xb = ops.normalize_rows(xc, want_f32=False, want_bf16=True)
     mc = None if mask is None else mask.to(torch.uint8).cuda()
-    om, oa, og = ops.score_max_bf16(qb, M, xb, Nv, R, mc, want_gap=True)
+    om, oa, og, fl = ops.score_max_bf16(qb, M, xb, Nv, R, mc, want_gap=True, flag_tau=3e-3)
     torch.cuda.synchronize()
+    # (0) flag bits == (gap < tau), and the flagged-pair runs list exactly those pairs
+    want_flag = og < 3e-3
+    bits = ((fl.cpu().numpy().view(np.uint32)[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(M, -1)[:, :Nv]
+    assert np.array_equal(bits.astype(bool), want_flag.cpu().numpy())
+    vb, ql, vc, slot = ops.select_flagged(fl, Nv)
+    vb_c, vc_c, ql_c, sl_c = vb.cpu().numpy(), vc.cpu().numpy(), ql.cpu().numpy(), slot.cpu().numpy()
+    assert int(vc_c.sum()) == int(want_flag.sum())
+    for n in range(Nv):
+        run = slice(int(vb_c[n]), int(vb_c[n]) + int(vc_c[n]))
+        assert sorted(ql_c[run].tolist()) == np.nonzero(want_flag.cpu().numpy()[:, n])[0].tolist()
+        assert np.array_equal(sl_c[run], ql_c[run].astype(np.int64) * Nv + n)
     # (1) vs fp32 oracle: north_star tolerance
     assert (om.cpu() - s_ref).abs().max() <= BF16_TOL
     # (2) vs fp32 evaluation of the same bf16 operands: accumulate-order noise only

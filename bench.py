@@ -132,6 +132,24 @@ def synth_encoded(shape, device, shard_seed, dkd_model_cls):
     return model, [torch.cat(inher), torch.cat(explore)], mask, [torch.cat(qi), torch.cat(qe)]
 
 
+def synth_c4(shape, device, shard_seed, nq=None):
+    """BASELINE.json configs[3]: clip features generated directly at D = H on the device, N(0,1),
+    seed = shard id; queries N(0,1) identical on every rank; key/value projections N(0, 0.02) like
+    reset_parameters (method/model.py:80-93).  The 32 downsampled frames ARE the frames (L = T = 32)."""
+    Nv, L, H = shape["Nv"], shape["L"], shape["H"]
+    nq = shape["Nq"] if nq is None else nq
+    g = torch.Generator(device=device).manual_seed(1000 + shard_seed)
+    frames = [torch.empty(Nv, L, H, device=device).normal_(generator=g) for _ in range(2)]
+    mask = torch.ones(Nv, L, device=device)
+    gq = torch.Generator(device=device).manual_seed(5_000_000)
+    qs = [torch.empty(nq, H, device=device).normal_(generator=gq) for _ in range(2)]
+    gp = torch.Generator(device=device).manual_seed(7)
+    params = [(torch.empty(H, H, device=device).normal_(0.0, 0.02, generator=gp), torch.zeros(H, device=device),
+               torch.empty(H, H, device=device).normal_(0.0, 0.02, generator=gp), torch.zeros(H, device=device))
+              for _ in range(2)]
+    return frames, mask, qs, params
+
+
 # ------------------------------------------------------------------------------------------------
 class CpuBaseline:
     """The oracle port of the reference's CPU eval loop on a bounded sample of the same workload:
@@ -146,12 +164,16 @@ class CpuBaseline:
         torch.set_num_threads(self.threads)
         sub = dict(shape)
         sub["Nq"] = max_queries
-        model, self.frames, self.mask, self.qs = synth_encoded(sub, torch.device("cpu"), 0, DLDKD)
-        if workload == "tvr_two_scale":
+        if workload == "c4_stream":
+            self.frames, self.mask, self.qs, params = synth_c4(sub, torch.device("cpu"), 0)
+        else:
+            model, self.frames, self.mask, self.qs = synth_encoded(sub, torch.device("cpu"), 0, DLDKD)
+            params = model.attention_params()
+        if workload != "tvr_frame":
             with torch.no_grad():
                 lengths = self.mask.sum(1).long()
                 self.props, self.keys, self.vals = [], [], []
-                for f, (kw, kb, vw, vb) in zip(self.frames, model.attention_params()):
+                for f, (kw, kb, vw, vb) in zip(self.frames, params):
                     self.props.append(O.build_proposals(O.downsample_clips(f, lengths, shape["T"])))
                     self.keys.append(torch.nn.functional.linear(f, kw, kb))
                     self.vals.append(torch.nn.functional.linear(f, vw, vb))
@@ -162,7 +184,7 @@ class CpuBaseline:
         qs = [q[:sample_queries] for q in self.qs]
         with torch.no_grad():
             t0 = time.perf_counter()
-            if self.workload == "tvr_two_scale":
+            if self.workload != "tvr_frame":
                 O.cpu_eval_two_scale(qs, self.props, self.keys, self.vals, self.mask, bsz=50, K=K_TOP)
             else:
                 O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
@@ -185,7 +207,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dkd_b200", choices=["dkd_b200", "reference"])
-    ap.add_argument("--workload", default="tvr_two_scale", choices=["tvr_two_scale", "tvr_frame"])
+    ap.add_argument("--workload", default="tvr_two_scale", choices=["tvr_two_scale", "tvr_frame", "c4_stream"])
+    ap.add_argument("--c4-videos", type=int, default=125_000, help="c4_stream: videos per GPU (1 M / 8)")
+    ap.add_argument("--c4-queries", type=int, default=100_000)
+    ap.add_argument("--chunk-videos", type=int, default=8192, help="c4_stream: videos per streamed chunk")
+    ap.add_argument("--query-batch", type=int, default=16384, help="c4_stream: queries per scoring call")
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
@@ -196,11 +222,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    shape = dict(TVR)
-    head = "two_scale" if args.workload == "tvr_two_scale" else "frame"
+    stream = args.workload == "c4_stream"
+    if stream:
+        # BASELINE.json configs[3]: 1 M videos x 32 downsampled frames over 8 GPUs = 125 k videos per GPU
+        shape = dict(Nv=args.c4_videos, L=32, Dv=None, Nq=args.c4_queries, Lq=None, Dq=None, H=384, T=32)
+    else:
+        shape = dict(TVR)
+    head = "frame" if args.workload == "tvr_frame" else "two_scale"
     cfg_common = {"workload": args.workload, "videos_per_gpu": shape["Nv"], "frames": shape["L"],
                   "visual_dim": shape["Dv"], "queries": shape["Nq"], "hidden": shape["H"], "branches": 2,
                   "top_k": K_TOP, "l2": "inputs larger than L2 (bf16 corpus operand 884 MB/branch)"}
+    if stream:
+        cfg_common.update(chunk_videos=args.chunk_videos, query_batch=args.query_batch,
+                          l2="inputs larger than L2 (resident clips 6.1 GB/branch; 3.3 GB bf16 operand per chunk)")
+    # the CPU legs run a bounded sample: a corpus slice for the streamed config (the full shard's proposals
+    # would need 100 GB of host memory), the full corpus otherwise
+    cpu_shape = dict(shape, Nv=min(shape["Nv"], 2048)) if stream else shape
 
     import __graft_entry__ as ge
     ge.load_package()
@@ -210,19 +247,19 @@ def main():
         if rank != 0:
             return
         nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
-        cpu = CpuBaseline(shape, args.workload, nq)
+        cpu = CpuBaseline(cpu_shape, args.workload, nq)
         first = cpu.run(50)                                     # untimed: also sizes the sample
         for _ in range(max(args.warmup - 1, 0)):
             cpu.run(50)
         # keep the whole run within a few minutes: K steps x sample <= ~200 s of CPU work
-        budget_q = int(first["value"] * (200.0 / max(args.steps, 1)) / shape["Nv"]) // 50 * 50
+        budget_q = int(first["value"] * (200.0 / max(args.steps, 1)) / cpu_shape["Nv"]) // 50 * 50
         nq = max(50, min(nq, budget_q))
         vals, last = [], None
         for _ in range(max(args.steps, 1)):
             last = cpu.run(nq)
             vals.append(last["value"])
         v = float(np.mean(vals))
-        sec = float(np.mean([nq * shape["Nv"] / x for x in vals]))
+        sec = float(np.mean([nq * cpu_shape["Nv"] / x for x in vals]))
         line = {"impl": "reference", "metric": "query-video pairs scored+ranked/sec", "value": v, "unit": "pairs/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -247,25 +284,39 @@ def main():
     from dkd_b200.model import DLDKD
     _lib.load()
 
-    model, frames, mask, qs = synth_encoded(shape, dev, rank, DLDKD)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
-                               T=shape["T"], heads=(head,), id_base=rank * shape["Nv"])
-    e1.record()
-    torch.cuda.synchronize()
-    prep_ms = e0.elapsed_time(e1)
-    del frames
-    qs = [q.contiguous() for q in qs]
     Nq, Nv = shape["Nq"], shape["Nv"]
+    if stream:
+        # the shard stays resident as encoded clips; operands are rebuilt chunk by chunk INSIDE the step
+        frames, mask, qs, attn = synth_c4(shape, dev, rank)
+        torch.cuda.synchronize()
+        prep_ms, pc = None, None
 
-    def step(q_dev):
-        pq = engine.prepare_queries(q_dev)
-        s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision="bf16", rescore=True, Kc=K_CAND)
-        if world > 1:
-            s, i = engine.merge_shards(s, i)
-        return s, i
+        def step(q_dev, precision="bf16"):
+            pqs = engine.split_queries(q_dev, args.query_batch)
+            chunks = engine.iter_chunks(frames, mask, args.chunk_videos, id_base=rank * Nv)
+            s, i = engine.rank_streamed(chunks, pqs, attn, K=K_TOP, T=shape["T"], precision=precision, Kc=K_CAND)
+            if world > 1:
+                s, i = engine.merge_shards(s, i)
+            return s, i
+    else:
+        model, frames, mask, qs = synth_encoded(shape, dev, rank, DLDKD)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                                   T=shape["T"], heads=(head,), id_base=rank * shape["Nv"])
+        e1.record()
+        torch.cuda.synchronize()
+        prep_ms = e0.elapsed_time(e1)
+        del frames
+        qs = [q.contiguous() for q in qs]
+
+        def step(q_dev, precision="bf16"):
+            pq = engine.prepare_queries(q_dev)
+            s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision=precision, rescore=True, Kc=K_CAND)
+            if world > 1:
+                s, i = engine.merge_shards(s, i)
+            return s, i
 
     def barrier():
         if world > 1:
@@ -340,11 +391,8 @@ def main():
            "boundary": "encoded query vectors in pinned host memory -> engine.rank -> top-100 (score, id) in host memory"}
 
     # ---- parity of the timed result: bf16+rescore top-100 == exact fp32 path top-100 (first 512 queries)
-    nchk = 512
-    pq_chk = engine.prepare_queries([q[:nchk] for q in qs])
-    s_ex, i_ex = engine.rank(pc, pq_chk, K=K_TOP, head=head, precision="exact")
-    if world > 1:
-        s_ex, i_ex = engine.merge_shards(s_ex, i_ex)
+    nchk = min(512, Nq)
+    s_ex, i_ex = step([q[:nchk] for q in qs], precision="exact")
     parity = {"queries_checked": nchk,
               "top100_ids_identical_to_exact_fp32": bool(torch.equal(i_ex, top_i[:nchk])),
               "top100_scores_identical": bool(torch.equal(s_ex, top_s[:nchk]))}
@@ -353,7 +401,10 @@ def main():
         pk = peaks()
         P = ops.num_proposals(shape["T"])
         R = P if head == "two_scale" else shape["L"]
-        flops_launch = 2.0 * Nq * Nv * R * shape["H"]
+        # algorithmic flops of one branch's contraction over the whole step; the streamed config spreads them
+        # over (chunks x query batches) launches, so "per launch" is the average launch
+        n_launch_step = max(len(gemm_ms) // max(args.steps, 1), 1)
+        flops_launch = 2.0 * Nq * Nv * R * shape["H"] * 2 / n_launch_step
         gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
         achieved = flops_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_avg_ms else None
         traffic = None
@@ -366,7 +417,8 @@ def main():
                     "frac_of_sustained_peak": achieved / pk["bf16_sustained"] if achieved else None,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {pk['source']}",
                     "flops_per_launch": flops_launch, "launches_timed": len(gemm_ms), "avg_launch_ms": gemm_avg_ms,
-                    "share_of_step": (2 * gemm_avg_ms / ms_step) if gemm_avg_ms else None, "traffic": traffic}
+                    "share_of_step": (n_launch_step * gemm_avg_ms / ms_step) if gemm_avg_ms else None,
+                    "traffic": traffic}
         line = {"metric": "query-video pairs scored+ranked/sec", "value": value, "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -374,10 +426,11 @@ def main():
                                                     candidates=K_CAND, rescoring="exact fp32"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
-                "corpus_bytes": pc.nbytes(), "parity": parity}
+                "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
+                "parity": parity}
         if not args.no_cpu_baseline and world >= 1:
             nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
-            line["cpu_baseline"] = run_cpu_baseline(shape, args.workload, nq)
+            line["cpu_baseline"] = run_cpu_baseline(cpu_shape, args.workload, nq)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -79,7 +79,12 @@ __global__ void downsample_clips_kernel(const float* __restrict__ frames,
 // T=32, D=384); every window sum is a running fp32 sum over the window (the AvgPool1d order),
 // each lane holding D/32 features as bf16x2-friendly pairs.  Per window: one warp reduction
 // for the norm, one coalesced bf16 row store.
-template <int kPairs>  // D = 64 * kPairs
+// kMeans = false (the production path: bf16 rows + scale only) never forms the mean: with
+// scale = 1 / (w * ||sum / w||) = 1 / ||sum|| the normalised row is sum * scale, so a window costs one
+// division instead of 4 per feature pair (the IEEE divisions made the first version issue bound at
+// 1.7 TB/s).  kMeans = true also writes the un-normalised fp32 means with the exact sum / w division
+// (tests, small shapes).
+template <int kPairs, bool kMeans>  // D = 64 * kPairs
 __global__ void __launch_bounds__(512)
 build_proposals_kernel(const float* __restrict__ clips, int T, int D,
                        __nv_bfloat16* __restrict__ prop_bf16, float* __restrict__ prop_scale,
@@ -105,32 +110,29 @@ build_proposals_kernel(const float* __restrict__ clips, int T, int D,
     for (int w = 1; w <= T - s; ++w) {
       const float* row = &sclips[(s + w - 1) * D];
       float ss = 0.f;
-      float mean[2 * kPairs];
       const float fw = (float)w;
 #pragma unroll
       for (int j = 0; j < kPairs; ++j) {
         float2 v = *reinterpret_cast<const float2*>(&row[64 * j + 2 * lane]);
         acc[2 * j] = (w == 1) ? v.x : __fadd_rn(acc[2 * j], v.x);
         acc[2 * j + 1] = (w == 1) ? v.y : __fadd_rn(acc[2 * j + 1], v.y);
-        mean[2 * j] = __fdiv_rn(acc[2 * j], fw);
-        mean[2 * j + 1] = __fdiv_rn(acc[2 * j + 1], fw);
-        ss = fmaf(mean[2 * j], mean[2 * j], ss);
-        ss = fmaf(mean[2 * j + 1], mean[2 * j + 1], ss);
+        ss = fmaf(acc[2 * j], acc[2 * j], ss);
+        ss = fmaf(acc[2 * j + 1], acc[2 * j + 1], ss);
       }
       ss = warp_sum(ss);
-      const float denom = fmaxf(sqrtf(ss), 1e-12f);
+      // ||mean|| = ||sum|| / w, clamped at 1e-12 like F.normalize:  scale = 1 / (w * max(||sum|| / w, 1e-12))
+      const float scale = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), __fmul_rn(fw, 1e-12f)));
       const int p = prop_index(w, s, T);
       const int64_t ro = ((int64_t)n * P + p) * D;
-      if (prop_scale && lane == 0) prop_scale[(int64_t)n * P + p] = __fdiv_rn(1.0f, __fmul_rn(fw, denom));
+      if (prop_scale && lane == 0) prop_scale[(int64_t)n * P + p] = scale;
 #pragma unroll
       for (int j = 0; j < kPairs; ++j) {
-        if (prop_f32) {
+        if (kMeans && prop_f32) {
           *reinterpret_cast<float2*>(&prop_f32[ro + 64 * j + 2 * lane]) =
-              make_float2(mean[2 * j], mean[2 * j + 1]);
+              make_float2(__fdiv_rn(acc[2 * j], fw), __fdiv_rn(acc[2 * j + 1], fw));
         }
         if (prop_bf16) {
-          __nv_bfloat162 b = __floats2bfloat162_rn(__fdiv_rn(mean[2 * j], denom),
-                                                   __fdiv_rn(mean[2 * j + 1], denom));
+          __nv_bfloat162 b = __floats2bfloat162_rn(__fmul_rn(acc[2 * j], scale), __fmul_rn(acc[2 * j + 1], scale));
           *reinterpret_cast<__nv_bfloat162*>(&prop_bf16[ro + 64 * j + 2 * lane]) = b;
         }
       }
@@ -157,9 +159,12 @@ frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ v
   float (*sV)[64] = reinterpret_cast<float (*)[64]>(smem_tab);                        // kLmax x 64
   float (*sE)[33] = reinterpret_cast<float (*)[33]>(smem_tab + kLmax * 64);           // kLmax x 33
   float (*sA)[kLmax + 1] = reinterpret_cast<float (*)[kLmax + 1]>(smem_tab + kLmax * 64 + kLmax * 33);
-  const int n = blockIdx.x;
+  // chunk index fastest: the blocks of one video are launched together and share its val / E rows through L2
+  // (video-major launch order re-read val from DRAM once per chunk: 11 x the algorithmic bytes).
   const int P = T * (T + 1) / 2;
-  const int p0 = blockIdx.y * kPC;
+  const int nchunk = (P + kPC - 1) / kPC;
+  const int n = blockIdx.x / nchunk;
+  const int p0 = (blockIdx.x % nchunk) * kPC;
   int len = lengths[n];
   len = len < 1 ? 1 : (len > L ? L : len);
   const int tid = threadIdx.x;
@@ -299,9 +304,16 @@ template <int kPairs>
 static int launch_build_proposals(const float* clips, int Nv, int T, int D, uint16_t* pb, float* ps,
                                   float* pf, cudaStream_t st) {
   size_t smem = (size_t)T * D * sizeof(float);
-  DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  build_proposals_kernel<kPairs><<<Nv, 512, smem, st>>>(clips, T, D, reinterpret_cast<__nv_bfloat16*>(pb), ps, pf);
+  auto* bf = reinterpret_cast<__nv_bfloat16*>(pb);
+  if (pf) {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_proposals_kernel<kPairs, true><<<Nv, 512, smem, st>>>(clips, T, D, bf, ps, pf);
+  } else {
+    DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_proposals_kernel<kPairs, false><<<Nv, 512, smem, st>>>(clips, T, D, bf, ps, pf);
+  }
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }
@@ -330,7 +342,7 @@ template <int kChunks>
 static int launch_frame_table(const float* E, const float* val, const int32_t* lengths, int Nv, int L,
                               int T, int D, float* tf, uint16_t* tb, cudaStream_t st) {
   const int P = T * (T + 1) / 2;
-  dim3 grid(Nv, (P + kPC - 1) / kPC);
+  const unsigned grid = (unsigned)Nv * (unsigned)((P + kPC - 1) / kPC);
   const size_t smem = sizeof(float) * (kLmax * 64 + kLmax * 33 + kPC * (kLmax + 1));
   DKD_CUDA_TRY(cudaFuncSetAttribute(frame_attn_table_kernel<kChunks>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -257,3 +257,50 @@ def merge_shards(local_scores, local_ids, group=None, merge_fn=None):
         dist.all_gather(list(gs.unbind(0)), local_scores.contiguous(), group=group)
         dist.all_gather(list(gi.unbind(0)), local_ids.contiguous(), group=group)
     return merge_fn(gs, gi)
+
+
+# ------------------------------------------------------------------------------------------------
+# Streamed corpus (BASELINE.json configs[3]: 1 M videos x 32 clips, 100 k queries, 8 GPUs).
+# The prepared operands of a 125 k-video shard (prop_b + table_h + table_f: 2.4 MB per video and branch) do
+# not fit 180 GB, the encoded clips (49 KB per video and branch) do.  So the shard stays resident as encoded
+# frames and is scored chunk by chunk: build the chunk's operands, score every query batch against it, fold
+# the chunk's per-query top-K into the running top-K.  Operand building is ~2 % of a chunk's GEMM time at
+# 100 k queries, so nothing is gained by keeping more than one chunk of operands alive.
+def split_queries(q_by_branch, batch=16384):
+    """Encoded query vectors (per branch (Nq, D)) -> list of PreparedQueries of at most `batch` queries."""
+    Nq = q_by_branch[0].shape[0]
+    return [prepare_queries([q[lo: lo + batch] for q in q_by_branch]) for lo in range(0, max(Nq, 1), batch)]
+
+
+def iter_chunks(frames_by_branch, mask, chunk_videos=8192, id_base=0):
+    """Slice a resident shard of encoded frames into (frames_by_branch, mask, id_base) chunks."""
+    Nv = frames_by_branch[0].shape[0]
+    for lo in range(0, Nv, chunk_videos):
+        hi = min(lo + chunk_videos, Nv)
+        yield [f[lo:hi] for f in frames_by_branch], mask[lo:hi], id_base + lo
+
+
+def rank_streamed(chunks, pqs, attn_params=None, K=100, T=ops.T_CLIPS, head="two_scale", precision="bf16",
+                  rescore=True, Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU):
+    """Per-query top-K over a corpus presented as successive chunks of videos.
+
+    chunks: iterable of (frames_by_branch, mask, id_base) — e.g. iter_chunks() over a resident shard, or a
+    generator that reads / synthesises one chunk at a time.  pqs: list of PreparedQueries (split_queries).
+    Returns (scores (Nq, K), ids (Nq, K) int32): identical to rank() over the concatenated corpus, because every
+    (query, video) score is produced by the same kernels on the same rows and the ordering (score desc, id asc)
+    is total, so a merge of per-chunk top-K lists is the global top-K."""
+    running = [None] * len(pqs)
+    precisions = ("exact", "bf16") if precision == "bf16" else ("exact",)
+    for frames, mask, id_base in chunks:
+        pc = prepare_corpus(frames, mask, attn_params, T=T, heads=(head,), precisions=precisions, id_base=id_base)
+        for b, pq in enumerate(pqs):
+            s, i = rank(pc, pq, K=K, head=head, precision=precision, rescore=rescore, Kc=Kc, w_clip=w_clip,
+                        w_frame=w_frame, tau=tau)
+            if running[b] is None:
+                running[b] = (s, i)
+            else:
+                running[b] = ops.merge_topk(torch.stack([running[b][0], s]), torch.stack([running[b][1], i]))
+        del pc
+    if any(r is None for r in running):
+        raise ValueError("rank_streamed: the corpus has no chunks")
+    return torch.cat([r[0] for r in running]), torch.cat([r[1] for r in running])

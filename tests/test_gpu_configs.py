@@ -88,3 +88,34 @@ def test_config_sharded_rank_equals_unsharded(ops):
         li.append(i)
     ms, mi = ops.merge_topk(torch.stack(ls), torch.stack(li))
     assert torch.equal(mi, i_all) and torch.equal(ms, s_all)
+
+
+def test_config_streamed_corpus_equals_resident_corpus(ops):
+    """BASELINE.json configs[3] scaled to one test box: 20,000 videos x 32 clips (N(0,1) at D = 384), 3,000
+    queries, streamed in chunks of 4,096 videos with query batches of 1,024 (engine.rank_streamed):
+      * exact streamed top-100 == exact top-100 over the resident corpus (ids AND scores);
+      * tcgen05 + rescoring streamed top-100 == exact streamed top-100 for every query;
+      * two ranks' halves streamed separately + dkd_merge_topk == the whole corpus."""
+    import bench
+    from dkd_b200 import engine
+    dev = torch.device("cuda")
+    shape = dict(Nv=20_000, L=32, Nq=3_000, H=384, T=32)
+    frames, mask, qs, attn = bench.synth_c4(shape, dev, 0)
+    pqs = engine.split_queries(qs, 1024)
+    assert [p.M for p in pqs] == [1024, 1024, 952]
+    s_ex, i_ex = engine.rank_streamed(engine.iter_chunks(frames, mask, 4096), pqs, attn, K=100, precision="exact")
+    s_bf, i_bf = engine.rank_streamed(engine.iter_chunks(frames, mask, 4096), pqs, attn, K=100, precision="bf16")
+    same = (i_bf == i_ex).all(dim=1)
+    assert bool(same.all()), f"{int((~same).sum())} of {shape['Nq']} queries differ"
+    assert torch.equal(s_bf, s_ex)
+    pc = engine.prepare_corpus(frames, mask, attn, T=32, heads=("two_scale",), precisions=("exact",))
+    s_all, i_all = engine.rank(pc, engine.prepare_queries(qs), K=100, head="two_scale", precision="exact")
+    assert torch.equal(i_all, i_ex) and torch.equal(s_all, s_ex)
+    del pc
+    halves = []
+    for r in range(2):
+        lo, hi = engine.shard_range(shape["Nv"], r, 2)
+        halves.append(engine.rank_streamed(engine.iter_chunks([f[lo:hi] for f in frames], mask[lo:hi], 4096, id_base=lo),
+                                           pqs, attn, K=100, precision="bf16"))
+    ms, mi = ops.merge_topk(torch.stack([h[0] for h in halves]), torch.stack([h[1] for h in halves]))
+    assert torch.equal(mi, i_ex) and torch.equal(ms, s_ex)

@@ -172,3 +172,29 @@ def test_sharded_rank_equals_unsharded(ops):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_streamed_rank_equals_resident_rank(ops):
+    """engine.rank_streamed over ragged chunks (last chunk short, one chunk smaller than K) and ragged query
+    batches == engine.rank over the whole corpus, exact precision, both heads' worth of branches."""
+    from dkd_b200 import engine
+    Nv, L, D, M, K = 333, 64, 128, 150, 100
+    frames, mask, _ = synth.encoded_corpus(Nv, L, D, seed=41)
+    frames2, _, _ = synth.encoded_corpus(Nv, L, D, seed=42)
+    frames2 = frames2 * mask[:, :, None]
+    gen = torch.Generator().manual_seed(43)
+    params = [(0.05 * torch.randn(D, D, generator=gen), torch.zeros(D), 0.05 * torch.randn(D, D, generator=gen),
+               torch.zeros(D)) for _ in range(2)]
+    dev = torch.device("cuda")
+    fr = [frames.to(dev), frames2.to(dev)]
+    params = [tuple(t.to(dev) for t in p) for p in params]
+    qs = [synth.encoded_queries(M, D, seed=44).to(dev), synth.encoded_queries(M, D, seed=45).to(dev)]
+    pc = engine.prepare_corpus(fr, mask.to(dev), params, heads=("two_scale",), precisions=("exact",))
+    s_all, i_all = engine.rank(pc, engine.prepare_queries(qs), K=K, head="two_scale", precision="exact")
+    pqs = engine.split_queries(qs, 64)
+    assert [p.M for p in pqs] == [64, 64, 22]
+    s_st, i_st = engine.rank_streamed(engine.iter_chunks(fr, mask.to(dev), 128, id_base=0), pqs, params, K=K,
+                                      precision="exact")      # chunks of 128, 128, 77 (< K) videos
+    assert torch.equal(i_st, i_all) and torch.equal(s_st, s_all)
+    with pytest.raises(ValueError):
+        engine.rank_streamed(iter(()), pqs, params)

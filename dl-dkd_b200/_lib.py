@@ -42,6 +42,10 @@ PROTOTYPES = {
     "dkd_frame_fuse_csr": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P],
     "dkd_scatter_fuse": [_P, _P, _F, _F, _P, _P, _I, _L, _P, _P],
     "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "dkd_row_inv_norms": [_P, _L, _I, _F, _P, _P],
+    "dkd_train_sim_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "dkd_train_sim_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dkd_kl_curve_loss": [_P, _P, _P, _I, _I, _F, _P, _P, _P],
 }
 _RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64, "dkd_row_planes_bytes": c_int64}
 
@@ -77,7 +81,7 @@ def check(code: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3}  # (memsets are not counted)
+KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3, "dkd_train_sim_bwd": 2}  # (memsets are not counted)
 _launches = 0
 _timed_names = set()
 _timed_events = {}

@@ -11,8 +11,9 @@ projections are new), same method names and argument meaning:
     key_clip_guided_attention[_in_inference](...)           SURVEY §8 N4 (CUDA kernels)
 
 The encoders stay PyTorch (query independent or <1% of eval); everything from the
-encoded vectors onward runs in the hand-written kernels behind include/dkd_b200.h.  Inference
-only: the kernels define no backward.
+encoded vectors onward runs in the hand-written kernels behind include/dkd_b200.h.  The retrieval
+kernels are inference only; the training step (forward(batch), method/model.py:100-162) goes through
+train.py, whose similarity and KL kernels have hand-written backward passes.
 """
 import math
 
@@ -141,7 +142,26 @@ class DLDKD(nn.Module):
             self.exp_out_mapping_linear = nn.Linear(E, E)
             self.exp_key_mapping = nn.Linear(E, E)
             self.exp_val_mapping = nn.Linear(E, E)
+        # loss weights read by forward() (method/model.py:67-75)
+        self.weight = 1
+        self.kl_intra_weight = _cfg(opt, "kl_intra_weight", 0.1)
+        self.inher_nce_weight = _cfg(opt, "inher_nce_weight", 0.04)
+        self.explore_nce_weight = _cfg(opt, "explore_nce_weight", 0.04)
+        self.collection = _cfg(opt, "collection", None)
+        self.alpha = _cfg(opt, "alpha", 0.8)
+        self.belta = _cfg(opt, "belta", 0.8)
         self.reset_parameters()
+
+    def set_hard_negative(self, use_hard_negative, hard_pool_size):
+        """method/model.py:95-98."""
+        self.config.use_hard_negative = use_hard_negative
+        self.config.hard_pool_size = hard_pool_size
+
+    def forward(self, batch):
+        """Training step losses (method/model.py:100-162): same batch keys, returns (loss, dict of terms).
+        Similarity forward/backward and the KL term run in the kernels of csrc/dkd_train.cu (train.py)."""
+        from . import train
+        return train.forward_losses(self, batch)
 
     def reset_parameters(self):
         """N(0, initializer_range) linears/embeddings, LayerNorm = (1, 0), zero biases (method/model.py:80-93)."""

@@ -370,3 +370,61 @@ def scatter_fuse(a, b, wa, wb, csr, cand_scores):
     _lib.call("dkd_scatter_fuse", _p(a), _p(b), wa, wb, _p(slot), _p(vid_ptr), vid_ptr.numel() - 1, a.numel(),
               _p(cand_scores), _stream())
     return cand_scores
+
+
+# ------------------------------------------------------------------------------------------------
+# training-step similarity (BASELINE.json configs[4]); see train.py
+def row_inv_norms(x, eps=1e-12):
+    """1 / max(||row||, eps) for every D-vector of x -> (rows,) fp32."""
+    _chk(x, torch.float32, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    out = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    _lib.call("dkd_row_inv_norms", _p(x), rows, D, eps, _p(out), _stream())
+    return out
+
+
+def train_sim_fwd(q, x, rq, rx, mask=None, labels=None, want_unnorm=True):
+    """One pass of dots -> (max_n, arg_n, max_u | None, arg_u | None, curve | None); see include/dkd_b200.h."""
+    _chk(q, torch.float32, "q")
+    _chk(x, torch.float32, "x")
+    M, D = q.shape
+    N, L, _ = x.shape
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    if labels is not None:
+        _chk(labels, torch.int32, "labels")
+    dev = q.device
+    max_n = torch.empty((M, N), dtype=torch.float32, device=dev)
+    arg_n = torch.empty((M, N), dtype=torch.int32, device=dev)
+    max_u = torch.empty((M, N), dtype=torch.float32, device=dev) if want_unnorm else None
+    arg_u = torch.empty((M, N), dtype=torch.int32, device=dev) if want_unnorm else None
+    curve = torch.empty((M, L), dtype=torch.float32, device=dev) if labels is not None else None
+    _lib.call("dkd_train_sim_fwd", _p(q), _p(x), _p(rq), _p(rx), _p(mask), _p(labels), M, N, L, D, _p(max_n),
+              _p(arg_n), _p(max_u), _p(arg_u), _p(curve), _stream())
+    return max_n, arg_n, max_u, arg_u, curve
+
+
+def train_sim_bwd(q, x, rq, rx, mask, labels, max_n, arg_n, arg_u, curve, g_n, g_u, g_c, want_q=True, want_x=True):
+    M, D = q.shape
+    N, L, _ = x.shape
+    for name, g in (("g_max_n", g_n), ("g_max_u", g_u), ("g_curve", g_c)):
+        if g is not None:
+            _chk(g, torch.float32, name)
+    gq = torch.empty_like(q) if want_q else None
+    gx = torch.empty_like(x) if want_x else None
+    _lib.call("dkd_train_sim_bwd", _p(q), _p(x), _p(rq), _p(rx), _p(mask), _p(labels), M, N, L, D, _p(max_n),
+              _p(arg_n), _p(arg_u), _p(curve), _p(g_n), _p(g_u), _p(g_c), _p(gq), _p(gx), _stream())
+    return gq, gx
+
+
+def kl_curve_loss(pred, target, lens, temp):
+    """Per-query KL(softmax(target/temp) || softmax(pred/temp)) over the first lens[m] frames -> (loss (M,), dpred (M, L))."""
+    _chk(pred, torch.float32, "pred")
+    _chk(target, torch.float32, "target")
+    _chk(lens, torch.int32, "lens")
+    M, L = pred.shape
+    loss = torch.empty((M,), dtype=torch.float32, device=pred.device)
+    dpred = torch.empty((M, L), dtype=torch.float32, device=pred.device)
+    _lib.call("dkd_kl_curve_loss", _p(pred), _p(target), _p(lens), M, L, float(temp), _p(loss), _p(dpred), _stream())
+    return loss, dpred

@@ -10,9 +10,7 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
- *   - no allocation, no host synchronisation, no global state inside any call
- *     (exception: dkd_score_rank_host, the host-buffer convenience entry, which
- *     synchronises `stream` before returning);
+ *   - no allocation, no host synchronisation, no global state inside any call;
  *   - return value: 0 = ok, <0 = DKD_ERR_* (bad argument), >0 = cudaError_t;
  *   - dense score matrices are query-major: element (m, n) at out[m * ld + n];
  *   - "rows per video" R: the scoring kernels see the corpus as Nv * R rows of D
@@ -223,6 +221,40 @@ int dkd_scatter_fuse(const float* a, const float* b, float wa, float wb, const i
 /* Sort each query's K candidates (score desc, id asc) and keep the first K_out. */
 int dkd_sort_candidates(const float* cand_scores, const int32_t* cand_ids, int32_t M, int32_t K,
                         int32_t K_out, float* out_scores, int32_t* out_ids, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Training-step similarity (BASELINE.json configs[4]).  Replaces, inside DLDKD.forward
+ * (method/model.py:109-157), the back-to-back get_sim_scores (:307-329) / get_unnormalized_sim_scores (:331-350)
+ * calls on the same operands and the column gather of compute_kl_loss (:184-188), forward and backward.
+ *
+ * dkd_row_inv_norms: out[r] = 1 / max(||x_r||, eps) — the denominator of F.normalize (:318-319).
+ *
+ * dkd_train_sim_fwd: q (M, D) raw queries, x (N, L, D) raw frames, rq (M) / rx (N*L) their inverse norms,
+ *   mask (N, L) uint8 or NULL, labels (M) positive video of each query (needed for curve).  One pass of fp32 dots:
+ *     max_n[m, n] = max_l cos(q_m, x_nl), arg_n = first argmax      (masked frames score exactly -1e10)
+ *     max_u[m, n] = max_l q_m . x_nl,     arg_u = first argmax
+ *     curve[m, l] = cos(q_m, x_{labels[m], l})  (masked: -1e10) — rows[m, :, labels[m]] of the reference
+ *   Any output may be NULL.  L <= 128, D % 32 == 0, 16-byte aligned q / x.
+ *
+ * dkd_train_sim_bwd: gradients of a scalar loss with respect to q and x given the upstream gradients of max_n,
+ *   max_u (M, N) and curve (M, L) (any may be NULL): the max routes to its argmax frame, masked frames get none,
+ *   cos differentiates through both norms.  grad_q (M, D) / grad_x (N, L, D) are overwritten (either may be
+ *   NULL).  Deterministic (no atomics).  D <= 512.
+ *
+ * dkd_kl_curve_loss: loss[m] = KL(softmax(target[m, :len] / temp) || softmax(pred[m, :len] / temp)), len = lens[m]
+ *   (F.kl_div(..., reduction='sum') per query, method/model.py:190-195), dpred = d loss[m] / d pred[m, l]
+ *   (zero beyond len).  L <= 128.
+ */
+int dkd_row_inv_norms(const float* x, int64_t rows, int32_t D, float eps, float* out, void* stream);
+int dkd_train_sim_fwd(const float* q, const float* x, const float* rq, const float* rx, const uint8_t* mask,
+                      const int32_t* labels, int32_t M, int32_t N, int32_t L, int32_t D, float* max_n,
+                      int32_t* arg_n, float* max_u, int32_t* arg_u, float* curve, void* stream);
+int dkd_train_sim_bwd(const float* q, const float* x, const float* rq, const float* rx, const uint8_t* mask,
+                      const int32_t* labels, int32_t M, int32_t N, int32_t L, int32_t D, const float* max_n,
+                      const int32_t* arg_n, const int32_t* arg_u, const float* curve, const float* g_max_n,
+                      const float* g_max_u, const float* g_curve, float* grad_q, float* grad_x, void* stream);
+int dkd_kl_curve_loss(const float* pred, const float* target, const int32_t* lens, int32_t M, int32_t L,
+                      float temp, float* loss, float* dpred, void* stream);
 
 #ifdef __cplusplus
 }

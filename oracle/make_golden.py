@@ -111,11 +111,69 @@ def golden_tiny_eval(M):
         map_fused=np.array(map_fu), t2v_ptr=t2v_ptr, t2v_ids=np.array(t2v_ids, np.int32), **sd)
 
 
+def golden_train_step(M):
+    """DLDKD.forward + backward of the unmodified reference on a tiny batch (BASELINE.json configs[4] in small):
+    loss terms and every parameter gradient, for three settings — soft labels + hard negatives (deterministic),
+    soft labels + sampled negatives (torch.manual_seed fixes the draws), hard labels + hard negatives."""
+    rm, _, _ = M
+    Dv, Dq, H, Lc, Lq, Dt = 48, 40, 64, 16, 8, 32
+    B, caps = 6, 3
+    cfg = ref_shim.model_config(Dv, Dq, hidden=H, n_heads=4, max_ctx_l=Lc, max_desc_l=Lq)
+    cfg.input_drop = 0.0
+    cfg.drop = 0.0
+    opt = ref_shim.options()
+    torch.manual_seed(0)
+    model = rm.DLDKD(cfg, opt)
+    g = torch.Generator().manual_seed(321)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+    model.train()
+    lens = torch.tensor([16, 3, 9, 16, 12, 5])
+    vmask = (torch.arange(Lc)[None] < lens[:, None]).float()
+    vids = torch.randn(B, Lc, Dv, generator=g) * vmask[:, :, None]
+    tv = torch.randn(B, Lc, Dt, generator=g) * vmask[:, :, None]
+    labels = [i for i in range(B) for _ in range(caps)]
+    nq = len(labels)
+    qlen = torch.randint(2, Lq + 1, (nq,), generator=g)
+    qmask = (torch.arange(Lq)[None] < qlen[:, None]).float()
+    txt = torch.randn(nq, Lq, Dq, generator=g) * qmask[:, :, None]
+    tt = torch.randn(nq, 1, Dt, generator=g)
+    batch = dict(text_labels=labels, student_videos=vids, student_videos_mask=vmask, student_text=txt,
+                 student_text_mask=qmask, teacher_text=tt, teacher_videos=tv)
+    out = dict(dims=np.array([Dv, Dq, H, Lc, Lq, Dt, B, caps], np.int64), labels=np.array(labels, np.int64),
+               videos=vids.numpy(), vmask=vmask.numpy(), teacher_videos=tv.numpy(), text=txt.numpy(),
+               qmask=qmask.numpy(), teacher_text=tt.numpy())
+    out.update({"sd." + k: v.detach().numpy().copy() for k, v in model.state_dict().items()})
+    terms = ["loss_overall", "inher_trip", "inher_nce", "explore_trip", "explore_nce", "kl", "kl_intra"]
+    for tag, style, hard, seed in (("soft_hard", "soft", True, None), ("soft_rand", "soft", False, 123),
+                                   ("hard_hard", "hard", True, None)):
+        cfg.label_style = style
+        model.set_hard_negative(hard, 1 if hard else 20)
+        model.zero_grad()
+        if seed is not None:
+            torch.manual_seed(seed)
+        loss, d = model(batch)
+        loss.backward()
+        out[f"{tag}.terms"] = np.array([float(d[k]) for k in terms], np.float64)
+        for k, p in model.named_parameters():
+            out[f"{tag}.grad.{k}"] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    # similarity intermediates of the inheritance branch (encoded features -> scores), for the kernel-level test
+    with torch.no_grad():
+        ctx_i, _ = model.encode_context(vids, vmask)
+        q_i, _ = model.encode_query(txt, qmask)
+        s, rows = rm.DLDKD.get_sim_scores(q_i, ctx_i, vmask)
+        u = rm.DLDKD.get_unnormalized_sim_scores(q_i, ctx_i, vmask)
+    out.update(enc_ctx=ctx_i.numpy(), enc_q=q_i.numpy(), sim_max=s.numpy(), sim_rows=rows.numpy(), sim_unnorm=u.numpy())
+    np.savez_compressed(os.path.join(OUT, "ref_train_step.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     mods = ref_shim.load()
     golden_sim_scores(mods)
     golden_avg_fixed(mods)
     golden_tiny_eval(mods)
+    golden_train_step(mods)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

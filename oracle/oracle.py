@@ -272,3 +272,113 @@ def cpu_eval_frame_head(q_by_branch, frames_by_branch, mask, bsz=50, K=100):
     fused = sc[0] if len(sc) == 1 else fuse_branches(sc[0], sc[1])
     order = np.stack([np.argsort(-fused[i])[:K] for i in range(fused.shape[0])])
     return fused, order
+
+
+# ----------------------------------------------------------------------------------- (a-REF) training step
+# Restatement of the loss side of DLDKD.forward (method/model.py:100-197, :352-388) and of clip_nce /
+# clip_nce_soft (method/model_components.py:106-233), from the ENCODED vectors onward, differentiable (plain
+# torch autograd provides the expected gradients).  PINNED by tests/golden/ref_train_step.npz (loss terms and
+# parameter gradients of the unmodified reference; oracle/make_golden.py:golden_train_step).
+def kl_frame_score(predict_rows, target_rows, mask, labels, temp=0.2):
+    """compute_kl_loss(mode='frame_score'), method/model.py:184-197.  *_rows (M, L, N)."""
+    loss = 0
+    for i, x in enumerate(labels):
+        feat_len = int((mask[x] > 0).sum())
+        p = F.log_softmax(predict_rows[i, :feat_len, x] / temp, dim=-1)
+        t = F.softmax(target_rows[i, :feat_len, x] / temp, dim=-1)
+        loss = loss + F.kl_div(p, t, reduction="sum")
+    return loss
+
+
+def clip_triplet_loss(scores, labels, margin, use_hard_negative, hard_pool_size):
+    """get_clip_triplet_loss, method/model.py:352-388 (same order of torch.randint draws)."""
+    labels = np.array(labels)
+    v2t, t2v = scores.t(), scores
+    v2t_loss = 0
+    for i in range(v2t.shape[0]):
+        pos = torch.mean(v2t[i][np.where(labels == i)[0]])
+        neg, _ = torch.sort(v2t[i][np.where(labels != i)[0]], descending=True)
+        pick = neg[0] if use_hard_negative else neg[torch.randint(0, neg.shape[0], size=(1,))]
+        v2t_loss = v2t_loss + (margin + pick - pos).clamp(min=0).sum()
+    idx = torch.arange(t2v.shape[0])
+    pos = t2v[idx, labels]
+    masked = t2v.detach().clone()
+    masked[idx, labels] = 999
+    _, order = torch.sort(masked, descending=True, dim=1)
+    hi = min(1 + hard_pool_size, t2v.shape[1]) if use_hard_negative else t2v.shape[1]
+    neg = t2v[idx, order[idx, torch.randint(1, hi, size=(t2v.shape[0],))]]
+    return (margin + neg - pos).clamp(min=0).sum() / len(t2v) + v2t_loss / len(v2t)
+
+
+def _label_dict(labels):
+    d = {}
+    for index, label in enumerate(labels):
+        d.setdefault(label, []).append(index)
+    return d
+
+
+def clip_nce(labels, scores):
+    """clip_nce.forward, method/model_components.py:215-233 (reduction 'mean')."""
+    M, N = scores.shape
+    nom = torch.logsumexp(scores[torch.arange(M), torch.as_tensor(labels)].unsqueeze(1), dim=1)
+    den = torch.logsumexp(scores, dim=1)
+    vn, vd = [torch.zeros(()) for _ in range(N)], [torch.zeros(()) for _ in range(N)]
+    for i, qs in _label_dict(labels).items():
+        vn[i] = torch.logsumexp(scores[qs, i], dim=0)
+        vd[i] = torch.logsumexp(scores[:, i], dim=0)
+    return torch.mean(den - nom) + torch.mean(torch.stack(vd) - torch.stack(vn))
+
+
+def clip_nce_soft(labels, scores, sims, alpha, belta):
+    """clip_nce_soft.forward, method/model_components.py:111-208 (reduction 'mean')."""
+    import math
+    M, N = scores.shape
+    hardQ, hardV = math.floor(alpha * M), math.floor(alpha * N)
+    softQ, softV = M - hardQ, N - hardV
+    ld = _label_dict(labels)
+    I = torch.zeros(M, N)
+    for i, qs in ld.items():
+        I[qs, i] = 1
+    IQ = I.clone()
+    IQ[hardQ:] = torch.clamp((1 - belta) * torch.softmax(sims, dim=-1)[hardQ:] + belta * IQ[hardQ:], min=0)
+    IV = I.T.clone()
+    IV[hardV:] = torch.clamp((1 - belta) * torch.softmax(sims.T, dim=-1)[hardV:] + belta * IV[hardV:], min=0)
+    lse = torch.logsumexp(scores, dim=1, keepdim=True)
+    t_nom_h, t_den_h = (IQ[:hardQ] * scores[:hardQ]).sum(), (IQ[:hardQ] * lse[:hardQ]).sum()
+    t_nom_s, t_den_s = (IQ[hardQ:] * scores[hardQ:]).sum(), (IQ[hardQ:] * lse[hardQ:]).sum()
+    v_nom_h = v_den_h = v_nom_s = v_den_s = torch.zeros(())
+    for i in ld:
+        nom = torch.logsumexp(torch.log(IV[i] + 1e-12) + scores[:, i], dim=0)
+        den = torch.logsumexp(scores[:, i], dim=0)
+        if i < hardV:
+            v_nom_h, v_den_h = v_nom_h + nom, v_den_h + den
+        else:
+            v_nom_s, v_den_s = v_nom_s + nom, v_den_s + den
+    hard = soft = 0.0
+    if hardQ != 0 and hardV != 0:
+        hard = (t_den_h - t_nom_h) / hardQ + (v_den_h - v_nom_h) / hardV
+    if softQ != 0 and softV != 0:
+        soft = (t_den_s - t_nom_s) / softQ + (v_den_s - v_nom_s) / softV
+    return alpha * hard + (1 - alpha) * soft
+
+
+def train_losses(enc, labels, mask, margin=0.1, use_hard_negative=True, hard_pool_size=1, label_style="soft",
+                 alpha=0.8, belta=0.8, w_kl=0.1, w_inher_nce=0.04, w_explore_nce=0.04):
+    """Loss side of DLDKD.forward, method/model.py:113-157.  enc: dict of ENCODED tensors — teacher_q (M, Dt),
+    teacher_ctx (N, L, Dt), inher_q / explore_q (M, D), inher_ctx / explore_ctx (N, L, D).  Returns (loss, terms)."""
+    _, t_rows, _ = get_sim_scores(enc["teacher_q"], enc["teacher_ctx"], mask)
+    t_u = get_unnormalized_sim_scores(enc["teacher_q"], enc["teacher_ctx"], mask)
+    i_max, i_rows, _ = get_sim_scores(enc["inher_q"], enc["inher_ctx"], mask)
+    i_u = get_unnormalized_sim_scores(enc["inher_q"], enc["inher_ctx"], mask)
+    e_max, _, _ = get_sim_scores(enc["explore_q"], enc["explore_ctx"], mask)
+    e_u = get_unnormalized_sim_scores(enc["explore_q"], enc["explore_ctx"], mask)
+    t = {}
+    t["inher_trip"] = clip_triplet_loss(i_max, labels, margin, use_hard_negative, hard_pool_size)
+    t["inher_nce"] = w_inher_nce * (clip_nce_soft(labels, i_u, t_u, alpha, belta) if label_style == "soft"
+                                    else clip_nce(labels, i_u))
+    t["explore_trip"] = clip_triplet_loss(e_max, labels, margin, use_hard_negative, hard_pool_size)
+    t["explore_nce"] = w_explore_nce * (clip_nce_soft(labels, e_u, e_u, alpha, belta) if label_style == "soft"
+                                        else clip_nce(labels, e_u))
+    t["kl"] = w_kl * kl_frame_score(i_rows, t_rows, mask, labels, 0.2)
+    loss = t["inher_trip"] + t["inher_nce"] + t["kl"] + t["explore_trip"] + t["explore_nce"]
+    return loss, t

@@ -118,3 +118,60 @@ def test_oracle_against_live_reference():
     vm = [f"v{i}" for i in range(30)]
     qm = [f"v{i % 30}#enc#{i // 30}" for i in range(40)]
     assert O.get_gt(vm, qm) == re_.get_gt(vm, qm)
+
+
+TRAIN_TERMS = ["loss_overall", "inher_trip", "inher_nce", "explore_trip", "explore_nce", "kl", "kl_intra"]
+TRAIN_SETTINGS = {"soft_hard": ("soft", True, 1, None), "soft_rand": ("soft", False, 20, 123),
+                  "hard_hard": ("hard", True, 1, None)}
+
+
+def _train_fixture(dkd, device="cpu"):
+    """The tiny training batch of ref_train_step.npz + the model mirror carrying the reference's weights."""
+    from dkd_b200 import model as M
+    g = _load("ref_train_step.npz")
+    Dv, Dq, H, Lc, Lq = (int(v) for v in g["dims"][:5])
+    cfg = ref_shim.model_config(Dv, Dq, hidden=H, n_heads=4, max_ctx_l=Lc, max_desc_l=Lq)
+    cfg.input_drop = 0.0
+    cfg.drop = 0.0
+    m = M.DLDKD(cfg, ref_shim.options())
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("key_mapping" in k or "val_mapping" in k for k in missing)
+    m = m.to(device).train()
+    t = lambda k: torch.from_numpy(g[k]).to(device)
+    batch = dict(text_labels=[int(x) for x in g["labels"]], student_videos=t("videos"), student_videos_mask=t("vmask"),
+                 student_text=t("text"), student_text_mask=t("qmask"), teacher_text=t("teacher_text"),
+                 teacher_videos=t("teacher_videos"))
+    return g, m, batch
+
+
+@pytest.mark.parametrize("tag", list(TRAIN_SETTINGS))
+def test_train_losses_oracle_matches_reference_fixture(dkd, tag):
+    """oracle.train_losses on the encoder mirror's outputs reproduces the unmodified reference's DLDKD.forward:
+    every loss term, and (through plain autograd) every parameter gradient, for the three fixture settings."""
+    g, m, batch = _train_fixture(dkd)
+    style, hard, pool, seed = TRAIN_SETTINGS[tag]
+    labels, mask = batch["text_labels"], batch["student_videos_mask"]
+    ci, ce = m.encode_context(batch["student_videos"], mask)
+    qi, qe = m.encode_query(batch["student_text"], batch["student_text_mask"])
+    enc = dict(teacher_q=batch["teacher_text"].squeeze(), teacher_ctx=batch["teacher_videos"], inher_q=qi,
+               inher_ctx=ci, explore_q=qe, explore_ctx=ce)
+    if seed is not None:
+        torch.manual_seed(seed)
+    loss, terms = O.train_losses(enc, labels, mask, margin=0.1, use_hard_negative=hard, hard_pool_size=pool,
+                                 label_style=style)
+    ref = dict(zip(TRAIN_TERMS, g[f"{tag}.terms"]))
+    assert abs(float(loss) - ref["loss_overall"]) <= 2e-6 * max(1.0, abs(ref["loss_overall"]))
+    for k in ("inher_trip", "inher_nce", "explore_trip", "explore_nce", "kl"):
+        assert abs(float(terms[k]) - ref[k]) <= 2e-6 * max(1.0, abs(ref[k])), k
+    loss.backward()
+    for name, p in m.named_parameters():
+        if "key_mapping" in name or "val_mapping" in name:
+            continue
+        want = g[f"{tag}.grad.{name}"]
+        got = p.grad.numpy() if p.grad is not None else np.zeros_like(want)
+        assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), name
+    # the similarity intermediates of the fixture
+    s, rows, _ = O.get_sim_scores(qi.detach(), ci.detach(), mask)
+    assert np.abs(s.numpy() - g["sim_max"]).max() <= 2e-6
+    assert np.abs(O.get_unnormalized_sim_scores(qi.detach(), ci.detach(), mask).numpy() - g["sim_unnorm"]).max() <= 2e-5

@@ -201,13 +201,110 @@ def run_cpu_baseline(shape, workload, sample_queries, threads=None):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_c5_train(args, rank, world, dev):
+    """BASELINE.json configs[4] from the encoded vectors on: batch 128 videos x 128 frames, 5 captions each (640
+    queries), D = 384 (teacher 512): in-batch similarity x3 + triplet / soft-NCE / KL losses, forward + backward
+    (train.losses_from_encoded).  value = (query, video) pairs per second through the whole step."""
+    import types
+    from dkd_b200 import train, _lib
+    from tests import synth
+    N, L, D, Dt, caps = 128, 128, 384, 512, 5
+    M = N * caps
+    labels = [i // caps for i in range(M)]
+    ci, mask, _ = synth.encoded_corpus(N, L, D, seed=51 + rank)
+    ce, ct = synth.encoded_corpus(N, L, D, seed=152 + rank)[0] * mask[:, :, None], \
+        synth.encoded_corpus(N, L, Dt, seed=253 + rank)[0] * mask[:, :, None]
+    qi, qe, qt = (synth.encoded_queries(M, d, seed=54 + k) for k, d in enumerate((D, D, Dt)))
+    qi, qe, qt = qi + 0.5 * ci[labels, 0], qe + 0.5 * ce[labels, 0], qt + 0.5 * ct[labels, 0]
+    host = [t.contiguous().pin_memory() for t in (qt, ct, qi, ci, qe, ce)]
+    keys = ("teacher_q", "teacher_ctx", "inher_q", "inher_ctx", "explore_q", "explore_ctx")
+    model = types.SimpleNamespace(
+        config=types.SimpleNamespace(label_style="soft", margin=0.1, use_hard_negative=True, hard_pool_size=1),
+        double_branch=True, weight=1, kl_intra_weight=0.1, inher_nce_weight=0.04, explore_nce_weight=0.04,
+        alpha=0.8, belta=0.8)
+    mask_d = mask.to(dev)
+
+    def step(tensors):
+        enc = {k: (t.detach().requires_grad_(k.startswith(("inher", "explore")))) for k, t in zip(keys, tensors)}
+        loss, _ = train.losses_from_encoded(model, enc, labels, mask_d)
+        loss.backward()
+        return loss.detach()
+
+    resident = [t.to(dev) for t in host]
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    _lib.reset_counters()
+    step(resident)
+    launches = _lib.launch_count()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    timed = ("dkd_train_sim_fwd", "dkd_train_sim_bwd", "dkd_kl_curve_loss", "dkd_row_inv_norms")
+    _lib.set_timed(set(timed))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(resident)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.result()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    tr = _lib.timed_results()
+    fwd_ms = tr.get("dkd_train_sim_fwd", [])
+    kernels_ms = {k: {"calls_per_step": len(v) // max(args.steps, 1), "ms_per_step": float(np.sum(v)) / max(args.steps, 1)}
+                  for k, v in tr.items() if v}
+    _lib.set_timed(set())
+    out_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    e0.record()
+    for _ in range(args.steps):
+        out_loss.copy_(step([t.to(dev, non_blocking=True) for t in host]), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    # CPU baseline: the oracle's loop-for-loop restatement of the reference, forward + backward, all threads
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cpu_s = []
+    for _ in range(3):
+        leaves = {k: t.clone().requires_grad_(k.startswith(("inher", "explore"))) for k, t in zip(keys, (qt, ct, qi, ci, qe, ce))}
+        t0 = time.perf_counter()
+        ref, _ = O.train_losses(leaves, labels, mask, use_hard_negative=True, hard_pool_size=1, label_style="soft")
+        ref.backward()
+        cpu_s.append(time.perf_counter() - t0)
+    cpu_t = float(np.median(cpu_s))
+    got = float(step(resident))
+    pk = peaks()
+    flops = 2.0 * M * N * L * (D + D + Dt) / 3.0      # average launch of the three similarity passes
+    avg = float(np.mean(fwd_ms)) if fwd_ms else None
+    line = {"metric": "query-video pairs scored fwd+bwd/sec (training step, from encoded vectors)",
+            "value": M * N / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5_train", "videos": N, "frames": L, "queries": M, "hidden": D, "teacher_dim": Dt,
+                       "label_style": "soft", "hard_negative_pool": 1, "l2": "working set 60 MB, L2 resident (one batch)"},
+            "clocks": clocks,
+            "e2e": {"value": M * N / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host)), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "roofline": {"bound": "tensor", "kernel": "train_sim_fwd_kernel (fp32 SIMT dots, fused max / raw max / curve)",
+                         "achieved": flops / (avg * 1e-3) / 1e12 if avg else None, "peak": pk["bf16_burst"],
+                         "unit": "TFLOP/s", "frac": flops / (avg * 1e-3) / 1e12 / pk["bf16_burst"] if avg else None,
+                         "avg_launch_ms": avg, "launches_timed": len(fwd_ms), "traffic": None,
+                         "note": "fp32-exact SIMT kernel: its own ceiling is the 72 TFLOP/s fp32 FMA pipe, not the bf16 tensor peak"},
+            "kernels_ms": kernels_ms,
+            "parity": {"loss": got, "oracle_loss": float(ref), "abs_diff": abs(got - float(ref))},
+            "cpu_baseline": {"value": M * N / cpu_t, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"the same batch, oracle.train_losses forward+backward, median of 3 ({cpu_t:.2f} s)"}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dkd_b200", choices=["dkd_b200", "reference"])
-    ap.add_argument("--workload", default="tvr_two_scale", choices=["tvr_two_scale", "tvr_frame", "c4_stream"])
+    ap.add_argument("--workload", default="tvr_two_scale", choices=["tvr_two_scale", "tvr_frame", "c4_stream", "c5_train"])
     ap.add_argument("--c4-videos", type=int, default=125_000, help="c4_stream: videos per GPU (1 M / 8)")
     ap.add_argument("--c4-queries", type=int, default=100_000)
     ap.add_argument("--chunk-videos", type=int, default=8192, help="c4_stream: videos per streamed chunk")
@@ -215,6 +312,7 @@ def main():
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="timed steps of the e2e leg (default max(3, steps/2))")
     args = ap.parse_args()
     if args.impl == "dkd_b200" and not args.profile:
         args.warmup = max(args.warmup, 3)
@@ -275,6 +373,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.workload == "c5_train":          # single-GPU secondary workload (replicas only: one batch per GPU)
+        if rank == 0:
+            bench_c5_train(args, rank, world, dev)
+        return
     import torch.distributed as dist
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -369,10 +471,10 @@ def main():
         out_s.copy_(s, non_blocking=True)
         out_i.copy_(i, non_blocking=True)
 
-    for _ in range(2):
+    for _ in range(1 if stream else 2):
         step_e2e()
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = args.e2e_steps or max(3, args.steps // 2)
     t0 = time.perf_counter()
     ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev2[0].record()

@@ -87,6 +87,9 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
     mask_u8 = (mask > 0).to(torch.uint8).contiguous()
     lengths = mask_u8.sum(dim=1).to(torch.int32).contiguous()
     pc = PreparedCorpus(Nv=Nv, L=L, D=D, T=T, id_base=id_base, mask_u8=mask_u8, lengths=lengths, heads=tuple(heads))
+    if Nv == 0:  # an empty shard (more ranks than videos): nothing to prepare, rank() returns padding
+        pc.branches = [BranchData() for _ in frames_by_branch]
+        return pc
     for bi, fr in enumerate(frames_by_branch):
         fr = fr.contiguous().float()
         bd = BranchData()
@@ -129,6 +132,9 @@ def prepare_queries(q_by_branch, want_bf16=True) -> PreparedQueries:
     M = q_by_branch[0].shape[0]
     Mpad = ops.round_up(max(M, 1), 256)  # 2 x 128: CTA pairs own two query tiles
     qn, qb, qh = [], [], []
+    if M == 0:
+        return PreparedQueries(M=0, Mpad=Mpad, qn=[q.float() for q in q_by_branch], qb=[None] * len(q_by_branch),
+                               qh=[None] * len(q_by_branch))
     for q in q_by_branch:
         f, b, h = ops.normalize_rows(q.contiguous().float(), want_f32=True, want_bf16=want_bf16, rows_pad=Mpad,
                                      want_f16=True)
@@ -207,6 +213,10 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     """
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
+    if pq.M == 0 or pc.Nv == 0:  # no queries / empty shard: K columns of padding (score -inf, id -1), like dkd_topk
+        dev = pc.mask_u8.device
+        return (torch.full((pq.M, K), float("-inf"), dtype=torch.float32, device=dev),
+                torch.full((pq.M, K), -1, dtype=torch.int32, device=dev))
     if head == "frame":
         sc = score_frame_head(pc, pq, precision)
         fused = sc[0][0] if nb == 1 else ops.fuse_scores(sc[0][0], sc[1][0], wbs[0], wbs[1])

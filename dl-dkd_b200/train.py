@@ -173,17 +173,14 @@ def clip_nce_soft_loss(labels, scores, sims, alpha, belta):
     return alpha * hard_loss + (1 - alpha) * soft_loss
 
 
-def forward_losses(model, batch):
-    """DLDKD.forward (method/model.py:100-162): same batch keys, same return value (loss, dict of terms)."""
+def losses_from_encoded(model, enc, labels, mask):
+    """The loss side of DLDKD.forward (method/model.py:113-157) on ENCODED vectors: enc = dict(teacher_q (M, Dt),
+    teacher_ctx (N, L, Dt), inher_q / explore_q (M, D), inher_ctx / explore_ctx (N, L, D)); `model` supplies the
+    loss weights and config (margin, hard negatives, label_style).  Returns (loss, dict of terms)."""
     cfg = model.config
-    labels = batch["text_labels"]
-    mask = batch["student_videos_mask"]
-    inher_ctx, explore_ctx = model.encode_context(batch["student_videos"], mask)
-    inher_q, explore_q = model.encode_query(batch["student_text"], batch["student_text_mask"])
-    teacher_q = batch["teacher_text"].squeeze()
     # teacher / inheritance / exploration scores: one fused pass each
-    _, t_max_u, t_curve = in_batch_similarity(teacher_q, batch["teacher_videos"], mask, labels)
-    i_max_n, i_max_u, i_curve = in_batch_similarity(inher_q, inher_ctx, mask, labels)
+    _, t_max_u, t_curve = in_batch_similarity(enc["teacher_q"], enc["teacher_ctx"], mask, labels)
+    i_max_n, i_max_u, i_curve = in_batch_similarity(enc["inher_q"], enc["inher_ctx"], mask, labels)
     soft = cfg.label_style == "soft"
     inher_trip = clip_triplet_loss(i_max_n, labels, cfg.margin, cfg.use_hard_negative, cfg.hard_pool_size)
     if soft:
@@ -192,7 +189,7 @@ def forward_losses(model, batch):
         inher_nce = model.inher_nce_weight * clip_nce_loss(labels, i_max_u)
     explore_trip = explore_nce = 0
     if model.double_branch:
-        e_max_n, e_max_u, _ = in_batch_similarity(explore_q, explore_ctx, mask, None)
+        e_max_n, e_max_u, _ = in_batch_similarity(enc["explore_q"], enc["explore_ctx"], mask, None)
         explore_trip = clip_triplet_loss(e_max_n, labels, cfg.margin, cfg.use_hard_negative, cfg.hard_pool_size)
         if soft:
             explore_nce = model.explore_nce_weight * clip_nce_soft_loss(labels, e_max_u, e_max_u, model.alpha, model.belta)
@@ -203,3 +200,13 @@ def forward_losses(model, batch):
     loss = inher_trip + inher_nce + kl + explore_trip + explore_nce
     return loss, {"loss_overall": float(loss), "inher_trip": inher_trip, "inher_nce": inher_nce,
                   "explore_trip": explore_trip, "explore_nce": explore_nce, "kl": kl, "kl_intra": kl_intra}
+
+
+def forward_losses(model, batch):
+    """DLDKD.forward (method/model.py:100-162): same batch keys, same return value (loss, dict of terms)."""
+    mask = batch["student_videos_mask"]
+    inher_ctx, explore_ctx = model.encode_context(batch["student_videos"], mask)
+    inher_q, explore_q = model.encode_query(batch["student_text"], batch["student_text_mask"])
+    enc = dict(teacher_q=batch["teacher_text"].squeeze(), teacher_ctx=batch["teacher_videos"], inher_q=inher_q,
+               inher_ctx=inher_ctx, explore_q=explore_q, explore_ctx=explore_ctx)
+    return losses_from_encoded(model, enc, batch["text_labels"], mask)

@@ -129,6 +129,7 @@ class PackedCorpus:
     def video(self, n, plane=0):
         """fp32 (length, D) tensor of one video (a copy)."""
         raw = np.ascontiguousarray(self.data[plane, n, : self.lengths[n]])
+        raw = raw.copy() if not raw.flags.writeable else raw
         t = torch.from_numpy(raw.view(np.int16) if self.dtype == "bf16" else raw)
         return (t.view(torch.bfloat16) if self.dtype == "bf16" else t).float()
 
@@ -180,7 +181,8 @@ def device_chunks(corpus, chunk_videos, device, lo=0, hi=None, id_base=None):
     """Generator of (frames_by_plane [fp32 (n, L, D) on `device`], mask (n, L), id_base) over videos [lo, hi):
     the chunk source of engine.rank_streamed for a corpus that lives on disk / in host memory.  Chunk i+1 is copied
     (mapped file -> pinned staging -> device, on a side stream) while the caller scores chunk i; two staging
-    buffers and two device buffers are recycled, guarded by events."""
+    buffers and two device buffers are recycled, guarded by events.  A yielded chunk may alias a recycled buffer:
+    it is valid until the next chunk is drawn (engine.rank_streamed consumes chunks that way)."""
     hi = corpus.Nv if hi is None else hi
     id_base = lo if id_base is None else id_base
     if hi <= lo:
@@ -204,7 +206,8 @@ def device_chunks(corpus, chunk_videos, device, lo=0, hi=None, id_base=None):
         if use_cuda and staged[b] is not None:
             staged[b].synchronize()              # the previous H2D out of this staging buffer has drained
         src = corpus.chunk(c_lo, c_hi)
-        staging[b][:, :n].copy_(torch.from_numpy(src.view(np.int16) if corpus.dtype == "bf16" else np.asarray(src)))
+        src = src.view(np.int16) if corpus.dtype == "bf16" else src
+        np.copyto(staging[b][:, :n].numpy(), src)              # mapped file -> pinned staging, one pass
         if use_cuda:
             with torch.cuda.stream(copy_stream):
                 if released[b] is not None:
@@ -225,8 +228,10 @@ def device_chunks(corpus, chunk_videos, device, lo=0, hi=None, id_base=None):
         if use_cuda:
             torch.cuda.current_stream(device).wait_event(staged[b])
         raw = dbuf[b][:, :n]
-        x = (raw.view(torch.bfloat16) if corpus.dtype == "bf16" else raw).float()     # fp32 working copy
+        x = (raw.view(torch.bfloat16) if corpus.dtype == "bf16" else raw).float()     # f32 files: a view of dbuf[b]
+        yield [x[p] for p in range(corpus.planes)], corpus.mask(c_lo, c_lo + n).to(device), id_base + (c_lo - lo)
+        # resumed: everything the consumer enqueued on the current stream for this chunk precedes this event,
+        # and only then may the copy stream overwrite device buffer b (a chunk is valid until the next one is drawn)
         if use_cuda:
             released[b] = torch.cuda.Event()
             released[b].record(torch.cuda.current_stream(device))
-        yield [x[p] for p in range(corpus.planes)], corpus.mask(c_lo, c_lo + n).to(device), id_base + (c_lo - lo)

@@ -46,8 +46,11 @@ PROTOTYPES = {
     "dkd_train_sim_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "dkd_train_sim_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dkd_kl_curve_loss": [_P, _P, _P, _I, _I, _F, _P, _P, _P],
+    "dkd_train_losses_workspace_floats": [_I, _I],
+    "dkd_train_losses": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _F, _F, _P, _P, _P, _P, _P],
 }
-_RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64, "dkd_row_planes_bytes": c_int64}
+_RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64, "dkd_row_planes_bytes": c_int64,
+             "dkd_train_losses_workspace_floats": c_int64}
 
 _lib = None
 
@@ -81,7 +84,8 @@ def check(code: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3, "dkd_train_sim_bwd": 2}  # (memsets are not counted)
+KERNELS_PER_CALL = {"dkd_candidates_to_csr": 3, "dkd_select_pairs_csr": 3, "dkd_train_sim_bwd": 2, "dkd_train_losses": 3,
+                    "dkd_train_losses_workspace_floats": 0}  # (memsets are not counted)
 _launches = 0
 _timed_names = set()
 _timed_events = {}

@@ -272,6 +272,186 @@ frame_attn_table_kernel(const float* __restrict__ E, const float* __restrict__ v
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Key-clip attention table, v2 (D <= 384): same phases, but the a.V product — 95 % of the work — runs on 8 x 8
+// register tiles over a whole-D val tile in shared memory.  v1 keeps 3 x 4 tiles and re-stages val per 64-feature
+// chunk: 4 LDS per 12 FMA, LSU bound at 70 % wavefront utilisation (profiles/r1_ncu_v13.md).  Here a thread
+// owns 8 proposals x 8 features (two float4 columns kD/2 apart, so every LDS.128 of a warp is contiguous):
+// 4 LDS.128 per 64 FMA, FMA bound.  Block = (video, 64 proposals), 8 * kD/8 threads, one block per SM
+// (val tile 128 x kD x 4 B = 192 KB at kD = 384 + transposed weights 32 KB = 224 KB of the 227 KB).
+constexpr int kPC2 = 64;  // proposals per block: 8 proposal groups x kD/8 feature groups = 12 warps at kD = 384 — a
+                          // multiple of the 4 schedulers (48 proposals = 9 warps left one scheduler with 3 warps and
+                          // the others waiting a third of the a.V loop at the barrier)
+constexpr int kAtLd = kPC2 + 4;  // sAt row stride: 16-byte aligned rows, 4-way instead of 32-way conflicts on the transposed stores
+template <int kD>
+__global__ void __launch_bounds__(kPC2 / 8 * kD / 8)
+frame_attn_table_v2_kernel(const float* __restrict__ E, const float* __restrict__ val,
+                           const int32_t* __restrict__ lengths, int L, int T,
+                           float* __restrict__ table_f32, __half* __restrict__ table_f16) {
+  constexpr int kFG = kD / 8;            // feature groups (threads per proposal group)
+  constexpr int kThreads = kPC2 / 8 * kFG;
+  extern __shared__ __align__(16) float smem_t2[];
+  float* sV = smem_t2;                               // kLmax x kD   (phase 3)
+  float* sAt = smem_t2 + kLmax * kD;                 // kLmax x kAtLd  transposed softmax weights
+  float (*sE)[33] = reinterpret_cast<float (*)[33]>(smem_t2);                     // phases 1-2 input, aliased on sV
+  static_assert(kLmax * 33 <= kLmax * kD, "the E tile must fit the val tile");
+  const int P = T * (T + 1) / 2;
+  const int nchunk = (P + kPC2 - 1) / kPC2;
+  const int n = blockIdx.x / nchunk;
+  const int p0 = (blockIdx.x % nchunk) * kPC2;
+  int len = lengths[n];
+  len = len < 1 ? 1 : (len > L ? L : len);
+  const int tid = threadIdx.x;
+
+  // async copies: the E tile (4-byte cp.async into the padded rows) and, behind it, every val row that does not
+  // alias the E tile — those land while phases 1-2 run
+  constexpr int kAliased = (kLmax * 33 + kD - 1) / kD;   // val rows overlapping the E tile
+  for (int i = tid; i < kLmax * 32; i += kThreads) {
+    const int l = i >> 5, c = i & 31;
+    if (l < L && c < T) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sE[l][c]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(&E[((int64_t)n * L + l) * T + c]));
+    } else {
+      sE[l][c] = 0.f;
+    }
+  }
+  asm volatile("cp.async.commit_group;");
+  for (int i = tid + kAliased * (kD / 4); i < len * (kD / 4); i += kThreads) {
+    const int l = i / (kD / 4), c4 = i % (kD / 4);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sV[l * kD + c4 * 4]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&val[((int64_t)n * L + l) * kD + c4 * 4]));
+  }
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // E tile landed
+  __syncthreads();
+  // phases 1 + 2, one warp per PAIR of adjacent proposals (same window length except at a length boundary): the
+  // windows are warp uniform, every lane owns 4 frames of both rows (8 independent LDS/FADD chains), the logits
+  // never leave registers.  v1 spends as many instructions inverting p -> (w, s) per (p, l) entry and walking
+  // dependent LDS chains as on the a.V product.  Same arithmetic as v1: sequential window sum, / w, accurate
+  // expf, e / sum.
+  {
+    constexpr int kQ = kLmax / 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int pr = warp; pr < kPC2 / 2; pr += kThreads / 32) {
+      int w[2], s0[2];
+      float lg[2][kQ];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int p = min(p0 + 2 * pr + r, P - 1);
+        int ww = 1, off = 0;
+        while (off + (T - ww + 1) <= p) { off += T - ww + 1; ++ww; }
+        w[r] = ww;
+        s0[r] = p - off;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) lg[r][k] = sE[lane + 32 * k][s0[r]];
+      }
+      const int wmax = max(w[0], w[1]);
+      for (int i = 1; i < wmax; ++i) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (i < w[r]) {
+#pragma unroll
+            for (int k = 0; k < kQ; ++k) lg[r][k] = __fadd_rn(lg[r][k], sE[lane + 32 * k][s0[r] + i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float fw = (float)w[r];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) {
+          lg[r][k] = __fdiv_rn(lg[r][k], fw);
+          if (lane + 32 * k < len) mx = fmaxf(mx, lg[r][k]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k) {
+          lg[r][k] = (lane + 32 * k < len) ? expf(lg[r][k] - mx) : 0.f;
+          sum += lg[r][k];
+        }
+        sum = warp_sum(sum);
+        const bool live = p0 + 2 * pr + r < P;
+#pragma unroll
+        for (int k = 0; k < kQ; ++k)
+          sAt[(lane + 32 * k) * kAtLd + 2 * pr + r] = live ? __fdiv_rn(lg[r][k], sum) : 0.f;
+      }
+    }
+  }
+  __syncthreads();   // sE dead from here: the first val rows may overwrite it
+  for (int i = tid; i < min(len, kAliased) * (kD / 4); i += kThreads) {
+    const int l = i / (kD / 4), c4 = i % (kD / 4);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sV[l * kD + c4 * 4]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&val[((int64_t)n * L + l) * kD + c4 * 4]));
+  }
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // phase 3: g[8 proposals][8 features] per thread
+  const int fg = tid % kFG, pg = tid / kFG;
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+  for (int l = 0; l < len; ++l) {
+    const float4 v0 = *reinterpret_cast<const float4*>(&sV[l * kD + fg * 4]);
+    const float4 v1 = *reinterpret_cast<const float4*>(&sV[l * kD + kD / 2 + fg * 4]);
+    const float4 w0 = *reinterpret_cast<const float4*>(&sAt[l * kAtLd + pg * 8]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&sAt[l * kAtLd + pg * 8 + 4]);
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(w[a], v[b], acc[a][b]);
+  }
+  // phase 4: row norms — partial sums per (proposal, feature group) into smem, summed in a fixed order
+  __syncthreads();   // all reads of sAt done: reuse it for the partials (kPC2 x kFG floats <= kLmax x kPC2)
+  float* part = sAt;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    float ss = 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) ss = fmaf(acc[a][b], acc[a][b], ss);
+    part[(pg * 8 + a) * kFG + fg] = ss;
+  }
+  __syncthreads();
+  float* snorm = part + kPC2 * kFG;       // kPC2 floats behind the partials
+  static_assert(kPC2 * kFG + kPC2 <= kLmax * kPC2, "partials + norms must fit the sAt region");
+  if (tid < kPC2) {
+    float ss = 0.f;
+    for (int k = 0; k < kFG; ++k) ss += part[tid * kFG + k];
+    snorm[tid] = fmaxf(sqrtf(ss), 1e-12f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int pl = pg * 8 + a;
+    const float denom = snorm[pl];
+    const int p = p0 + pl;
+    if (p >= P) continue;
+    const int64_t ro = ((int64_t)n * P + p) * kD;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = h * (kD / 2) + fg * 4;
+      float4 o = make_float4(__fdiv_rn(acc[a][4 * h + 0], denom), __fdiv_rn(acc[a][4 * h + 1], denom),
+                             __fdiv_rn(acc[a][4 * h + 2], denom), __fdiv_rn(acc[a][4 * h + 3], denom));
+      if (table_f32) *reinterpret_cast<float4*>(&table_f32[ro + col]) = o;
+      if (table_f16) {
+        __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(&table_f16[ro + col]) = pk;
+      }
+    }
+  }
+}
+
 }  // namespace dkd
 
 using namespace dkd;
@@ -352,6 +532,20 @@ static int launch_frame_table(const float* E, const float* val, const int32_t* l
   return DKD_OK;
 }
 
+template <int kD>
+static int launch_frame_table_v2(const float* E, const float* val, const int32_t* lengths, int Nv, int L, int T,
+                                 float* tf, uint16_t* tb, cudaStream_t st) {
+  const int P = T * (T + 1) / 2;
+  const unsigned grid = (unsigned)Nv * (unsigned)((P + kPC2 - 1) / kPC2);
+  const size_t smem = sizeof(float) * ((size_t)kLmax * kD + (size_t)kLmax * kAtLd);
+  DKD_CUDA_TRY(cudaFuncSetAttribute(frame_attn_table_v2_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  frame_attn_table_v2_kernel<kD><<<grid, kPC2 / 8 * kD / 8, smem, st>>>(E, val, lengths, L, T, tf,
+                                                                reinterpret_cast<__half*>(tb));
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
 extern "C" int dkd_frame_attn_table(const float* E, const float* val, const int32_t* lengths, int32_t Nv,
                                     int32_t L, int32_t T, int32_t D, float* table_f32,
                                     uint16_t* table_f16, void* stream) {
@@ -359,6 +553,8 @@ extern "C" int dkd_frame_attn_table(const float* E, const float* val, const int3
   if (L <= 0 || L > kLmax || T <= 0 || T > 32 || D % 64 != 0 || D > 512) return DKD_ERR_SHAPE;
   if (Nv == 0) return DKD_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (D == 384) return launch_frame_table_v2<384>(E, val, lengths, Nv, L, T, table_f32, table_f16, st);
+  if (D == 256) return launch_frame_table_v2<256>(E, val, lengths, Nv, L, T, table_f32, table_f16, st);
   switch (D / 64) {
     case 1: return launch_frame_table<1>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);
     case 2: return launch_frame_table<2>(E, val, lengths, Nv, L, T, D, table_f32, table_f16, st);

@@ -419,3 +419,312 @@ extern "C" int dkd_kl_curve_loss(const float* pred, const float* target, const i
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused triplet + NCE losses on the (M, N) in-batch score matrices, forward value AND gradient in one pass
+// (get_clip_triplet_loss method/model.py:352-388; clip_nce / clip_nce_soft method/model_components.py:106-233).
+// The reference builds these from ~150 small tensor ops and two Python loops over the videos; here a row kernel
+// (one warp per query), a column kernel (one block per video) and a 1-block reduction produce both loss terms and
+// d loss / d scores.  No float atomics: per-row / per-column partial losses are summed in a fixed order, every
+// gradient entry is written by the row kernel and updated by exactly one thread of the column kernel.
+namespace dkd {
+
+struct LossParams {
+  const float *s_n, *s_u, *sims;   // sims == nullptr: hard labels (clip_nce); sims == s_u: self distillation
+  const int32_t *labels, *t2v_draw, *v2t_pick;
+  int M, N;
+  float margin, alpha, belta;
+  int soft;                        // label_style == 'soft'
+  float *g_n, *g_u;                // (M, N) gradients of (triplet, nce) w.r.t. (s_n, s_u)
+  float *row_part, *col_part;      // (2, M) and (2, N) partial losses
+};
+
+__device__ __forceinline__ float lse_warp_row(const float* row, int N, int lane, float* mx_out) {
+  float mx = -INFINITY;
+  for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < N; j += 32) s += expf(row[j] - mx);
+  s = warp_sum(s);
+  *mx_out = mx;
+  return mx + logf(s);
+}
+
+// part weights of clip_nce_soft (reduction 'mean'): the hard part counts only if hardQ != 0 and hardV != 0, the soft
+// part only if softQ != 0 and softV != 0 (method/model_components.py:190-203)
+__device__ __forceinline__ void nce_parts(const LossParams& p, int& hardQ, int& hardV, float& wh, float& ws) {
+  hardQ = (int)floorf(p.alpha * (float)p.M);
+  hardV = (int)floorf(p.alpha * (float)p.N);
+  const bool hard_on = hardQ != 0 && hardV != 0;
+  const bool soft_on = (p.M - hardQ) != 0 && (p.N - hardV) != 0;
+  wh = hard_on ? p.alpha : 0.f;
+  ws = soft_on ? (1.f - p.alpha) : 0.f;
+}
+
+__global__ void __launch_bounds__(128)
+loss_rows_kernel(const LossParams p) {
+  extern __shared__ float smem_lr[];          // 4 warps x 2 rows of N
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= p.M) return;
+  float* rn = smem_lr + (size_t)warp * 2 * p.N;
+  float* ru = rn + p.N;
+  const int lab = p.labels[m];
+  for (int j = lane; j < p.N; j += 32) {
+    rn[j] = p.s_n[(int64_t)m * p.N + j];
+    ru[j] = p.s_u[(int64_t)m * p.N + j];
+  }
+  __syncwarp();
+  // ---- triplet, text -> video: positive vs the negative at position t2v_draw[m] of the descending order in which
+  // the positive (masked to 999) comes first
+  {
+    const int r = p.t2v_draw[m] - 1;
+    int pick = -1;
+    for (int j = lane; j < p.N; j += 32) {
+      if (j == lab) continue;
+      const float v = rn[j];
+      int c = 0;
+      for (int k = 0; k < p.N; ++k) {
+        if (k == lab) continue;
+        const float w = rn[k];
+        c += (w > v) || (w == v && k < j);
+      }
+      if (c == r) pick = j;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pick = max(pick, __shfl_xor_sync(0xffffffffu, pick, o));
+    float loss = 0.f;
+    bool active = false;
+    if (pick >= 0) {
+      const float d = p.margin + rn[pick] - rn[lab];
+      active = d > 0.f;
+      loss = active ? d / (float)p.M : 0.f;
+    }
+    const float g = active ? 1.f / (float)p.M : 0.f;
+    for (int j = lane; j < p.N; j += 32)
+      p.g_n[(int64_t)m * p.N + j] = (j == pick ? g : 0.f) - (j == lab ? g : 0.f);
+    if (lane == 0) p.row_part[m] = loss;
+  }
+  // ---- NCE, text -> video
+  {
+    float mx;
+    const float lse = lse_warp_row(ru, p.N, lane, &mx);
+    if (!p.soft) {  // clip_nce: mean over queries of lse - s[m, lab]
+      const float a = 1.f / (float)p.M;
+      for (int j = lane; j < p.N; j += 32)
+        p.g_u[(int64_t)m * p.N + j] = a * (expf(ru[j] - lse) - (j == lab ? 1.f : 0.f));
+      if (lane == 0) p.row_part[p.M + m] = a * (lse - ru[lab]);
+    } else {
+      int hardQ, hardV;
+      float wh, ws;
+      nce_parts(p, hardQ, hardV, wh, ws);
+      const bool soft_row = m >= hardQ;
+      const float a = soft_row ? ws / (float)(p.M - hardQ) : wh / (float)hardQ;
+      const float* z = p.sims + (int64_t)m * p.N;
+      float zl = 0.f, zmx;
+      if (soft_row) {
+        zmx = -INFINITY;
+        for (int j = lane; j < p.N; j += 32) zmx = fmaxf(zmx, z[j]);
+        zmx = warp_max(zmx);
+        float s = 0.f;
+        for (int j = lane; j < p.N; j += 32) s += expf(z[j] - zmx);
+        zl = zmx + logf(warp_sum(s));
+      }
+      // dot = sum_n IQ[n] s[n];  ps = sum_n P[n] s[n] (self-distillation term)
+      float dot = 0.f, ps = 0.f;
+      for (int j = lane; j < p.N; j += 32) {
+        const float one = (j == lab) ? 1.f : 0.f;
+        const float P = soft_row ? expf(z[j] - zl) : 0.f;
+        const float iq = soft_row ? fmaxf((1.f - p.belta) * P + p.belta * one, 0.f) : one;
+        dot = fmaf(iq, ru[j], dot);
+        ps = fmaf(P, ru[j], ps);
+      }
+      dot = warp_sum(dot);
+      ps = warp_sum(ps);
+      const bool self = soft_row && (p.sims == p.s_u);
+      for (int j = lane; j < p.N; j += 32) {
+        const float one = (j == lab) ? 1.f : 0.f;
+        const float P = soft_row ? expf(z[j] - zl) : 0.f;
+        const float iq = soft_row ? fmaxf((1.f - p.belta) * P + p.belta * one, 0.f) : one;
+        float g = expf(ru[j] - lse) - iq;                              // sum_n IQ = 1
+        if (self) g -= (1.f - p.belta) * P * (ru[j] - ps);
+        p.g_u[(int64_t)m * p.N + j] = a * g;
+      }
+      if (lane == 0) p.row_part[p.M + m] = a * (lse - dot);
+    }
+  }
+}
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int w = 0; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+loss_cols_kernel(const LossParams p) {
+  extern __shared__ float smem_lc[];          // 3 columns of M + 8 reduction slots
+  float* cn = smem_lc;
+  float* cu = cn + p.M;
+  float* cz = cu + p.M;
+  float* red = cz + p.M;
+  __shared__ int s_pick;
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool has_z = p.soft != 0;
+  for (int m = tid; m < p.M; m += blockDim.x) {
+    cn[m] = p.s_n[(int64_t)m * p.N + i];
+    cu[m] = p.s_u[(int64_t)m * p.N + i];
+    cz[m] = has_z ? p.sims[(int64_t)m * p.N + i] : 0.f;
+  }
+  if (tid == 0) s_pick = -1;
+  __syncthreads();
+  // ---- triplet, video -> text
+  float cnt_f = 0.f, possum = 0.f;
+  for (int m = tid; m < p.M; m += blockDim.x)
+    if (p.labels[m] == i) { cnt_f += 1.f; possum += cn[m]; }
+  const float cnt = block_reduce(cnt_f, red, false);
+  possum = block_reduce(possum, red, false);
+  const int r = p.v2t_pick[i];
+  for (int m = tid; m < p.M; m += blockDim.x) {
+    if (p.labels[m] == i) continue;
+    const float v = cn[m];
+    int c = 0;
+    for (int k = 0; k < p.M; ++k) {
+      if (p.labels[k] == i) continue;
+      const float w = cn[k];
+      c += (w > v) || (w == v && k < m);
+    }
+    if (c == r) s_pick = m;                   // ranks are distinct: one writer
+  }
+  __syncthreads();
+  const int pick = s_pick;
+  float trip = 0.f;
+  bool active = false;
+  if (cnt == 0.f) {
+    trip = __int_as_float(0x7fc00000);        // torch.mean of an empty slice (method/model.py:361) is nan
+  } else if (pick >= 0) {
+    const float d = p.margin + cn[pick] - possum / cnt;
+    active = d > 0.f;
+    trip = active ? d / (float)p.N : 0.f;
+  }
+  if (active) {
+    const float g = 1.f / (float)p.N;
+    for (int m = tid; m < p.M; m += blockDim.x) {
+      const bool pos = p.labels[m] == i;
+      if (pos || m == pick) p.g_n[(int64_t)m * p.N + i] += pos ? -g / cnt : g;
+    }
+  }
+  // ---- NCE, video -> text (only videos that own a caption: label_dict keys)
+  float nce = 0.f;
+  if (cnt > 0.f) {
+    float mxl = -INFINITY;
+    for (int m = tid; m < p.M; m += blockDim.x) mxl = fmaxf(mxl, cu[m]);
+    const float mx = block_reduce(mxl, red, true);
+    float sl = 0.f;
+    for (int m = tid; m < p.M; m += blockDim.x) sl += expf(cu[m] - mx);
+    const float den = mx + logf(block_reduce(sl, red, false));
+    if (!p.soft) {  // clip_nce: nominator = logsumexp over the video's own captions; mean over all N videos
+      float pl = 0.f;
+      for (int m = tid; m < p.M; m += blockDim.x)
+        if (p.labels[m] == i) pl += expf(cu[m] - mx);
+      const float nom = mx + logf(block_reduce(pl, red, false));
+      const float b = 1.f / (float)p.N;
+      for (int m = tid; m < p.M; m += blockDim.x) {
+        const float wpos = (p.labels[m] == i) ? expf(cu[m] - nom) : 0.f;
+        p.g_u[(int64_t)m * p.N + i] += b * (expf(cu[m] - den) - wpos);
+      }
+      nce = b * (den - nom);
+    } else {
+      int hardQ, hardV;
+      float wh, ws;
+      nce_parts(p, hardQ, hardV, wh, ws);
+      const bool soft_col = i >= hardV;
+      const float b = soft_col ? ws / (float)(p.N - hardV) : wh / (float)hardV;
+      float zl = 0.f;
+      if (soft_col) {
+        float zm = -INFINITY;
+        for (int m = tid; m < p.M; m += blockDim.x) zm = fmaxf(zm, cz[m]);
+        const float zmx = block_reduce(zm, red, true);
+        float zs = 0.f;
+        for (int m = tid; m < p.M; m += blockDim.x) zs += expf(cz[m] - zmx);
+        zl = zmx + logf(block_reduce(zs, red, false));
+      }
+      // nominator: logsumexp_m( log(IV[m] + 1e-12) + s[m] ), computed relative to mx (log(IV + eps) <= ~0)
+      float nl = 0.f;
+      for (int m = tid; m < p.M; m += blockDim.x) {
+        const float one = (p.labels[m] == i) ? 1.f : 0.f;
+        const float iv = soft_col ? fmaxf((1.f - p.belta) * expf(cz[m] - zl) + p.belta * one, 0.f) : one;
+        nl += (iv + 1e-12f) * expf(cu[m] - mx);
+      }
+      const float nsum = block_reduce(nl, red, false);
+      const float nom = mx + logf(nsum);
+      const bool self = soft_col && (p.sims == p.s_u);
+      float up = 0.f;                          // sum_m U[m] Pv[m],  U = W / (IV + eps) = exp(s - mx) / nsum
+      if (self) {
+        float ul = 0.f;
+        for (int m = tid; m < p.M; m += blockDim.x) ul += expf(cu[m] - mx) / nsum * expf(cz[m] - zl);
+        up = block_reduce(ul, red, false);
+      }
+      for (int m = tid; m < p.M; m += blockDim.x) {
+        const float one = (p.labels[m] == i) ? 1.f : 0.f;
+        const float Pv = soft_col ? expf(cz[m] - zl) : 0.f;
+        const float iv = soft_col ? fmaxf((1.f - p.belta) * Pv + p.belta * one, 0.f) : one;
+        const float e = expf(cu[m] - mx) / nsum;
+        float g = expf(cu[m] - den) - (iv + 1e-12f) * e;
+        if (self) g -= (1.f - p.belta) * Pv * (e - up);
+        p.g_u[(int64_t)m * p.N + i] += b * g;
+      }
+      nce = b * (den - nom);
+    }
+  }
+  if (tid == 0) {
+    p.col_part[i] = trip;
+    p.col_part[p.N + i] = nce;
+  }
+}
+
+// out[0] = triplet, out[1] = nce: fixed-order sums of the row and column partials (one block).
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part, int M, int N,
+                   float* __restrict__ out) {
+  __shared__ float red[8];
+  for (int t = 0; t < 2; ++t) {
+    float a = 0.f;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) a += row_part[t * M + m];
+    for (int n = threadIdx.x; n < N; n += blockDim.x) a += col_part[t * N + n];
+    const float s = block_reduce(a, red, false);
+    if (threadIdx.x == 0) out[t] = s;
+  }
+}
+
+}  // namespace dkd
+
+extern "C" int64_t dkd_train_losses_workspace_floats(int32_t M, int32_t N) { return 2 * ((int64_t)M + N); }
+
+extern "C" int dkd_train_losses(const float* s_n, const float* s_u, const float* sims, const int32_t* labels,
+                                const int32_t* t2v_draw, const int32_t* v2t_pick, int32_t M, int32_t N,
+                                float margin, int32_t soft, float alpha, float belta, float* out_terms,
+                                float* g_n, float* g_u, float* workspace, void* stream) {
+  if (!s_n || !s_u || !labels || !t2v_draw || !v2t_pick || !out_terms || !g_n || !g_u || !workspace) return DKD_ERR_ARG;
+  if (soft && !sims) return DKD_ERR_ARG;
+  if (M <= 0 || N <= 1 || N > 2048 || M > 8192) return DKD_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  LossParams p{s_n, s_u, soft ? sims : nullptr, labels, t2v_draw, v2t_pick, M, N, margin, alpha, belta, soft,
+               g_n, g_u, workspace, workspace + 2 * (int64_t)M};
+  const size_t smem_r = sizeof(float) * 4 * 2 * (size_t)N;
+  const size_t smem_c = sizeof(float) * (3 * (size_t)M + 8);
+  DKD_CUDA_TRY(cudaFuncSetAttribute(loss_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  loss_rows_kernel<<<(M + 3) / 4, 128, smem_r, st>>>(p);
+  DKD_LAUNCH_CHECK();
+  loss_cols_kernel<<<N, 256, smem_c, st>>>(p);
+  DKD_LAUNCH_CHECK();
+  loss_reduce_kernel<<<1, 256, 0, st>>>(p.row_part, p.col_part, M, N, out_terms);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}

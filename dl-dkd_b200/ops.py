@@ -428,3 +428,23 @@ def kl_curve_loss(pred, target, lens, temp):
     dpred = torch.empty((M, L), dtype=torch.float32, device=pred.device)
     _lib.call("dkd_kl_curve_loss", _p(pred), _p(target), _p(lens), M, L, float(temp), _p(loss), _p(dpred), _stream())
     return loss, dpred
+
+
+def train_losses(s_n, s_u, sims, labels, t2v_draw, v2t_pick, margin, soft, alpha, belta):
+    """Fused triplet + NCE losses of one branch -> (terms (2,) [triplet, nce], g_n (M, N), g_u (M, N))."""
+    _chk(s_n, torch.float32, "s_n")
+    _chk(s_u, torch.float32, "s_u")
+    if soft:
+        _chk(sims, torch.float32, "sims")
+    for name, t in (("labels", labels), ("t2v_draw", t2v_draw), ("v2t_pick", v2t_pick)):
+        _chk(t, torch.int32, name)
+    M, N = s_n.shape
+    dev = s_n.device
+    terms = torch.empty((2,), dtype=torch.float32, device=dev)
+    g_n = torch.empty((M, N), dtype=torch.float32, device=dev)
+    g_u = torch.empty((M, N), dtype=torch.float32, device=dev)
+    ws = torch.empty((int(_lib.load().dkd_train_losses_workspace_floats(M, N)),), dtype=torch.float32, device=dev)
+    _lib.call("dkd_train_losses", _p(s_n), _p(s_u), _p(sims) if soft else None, _p(labels), _p(t2v_draw), _p(v2t_pick),
+              M, N, float(margin), int(bool(soft)), float(alpha), float(belta), _p(terms), _p(g_n), _p(g_u), _p(ws),
+              _stream())
+    return terms, g_n, g_u

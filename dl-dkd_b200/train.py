@@ -8,13 +8,11 @@ What runs where
     reference materialises twice per branch never exists;
   * masked-softmax KL over that curve (:190-195) — one fused forward+backward kernel instead of a Python loop of
     M log_softmax / softmax / kl_div calls;
-  * triplet and (soft) NCE losses (:352-388, method/model_components.py:106-233) — vectorised PyTorch on the
-    (M, N) score matrices (82 k elements at batch 128 x 5 captions); the reference's per-video Python loops are
-    gone, the arithmetic and the order of torch.randint draws are kept.
+  * triplet and (soft) NCE losses (:352-388, method/model_components.py:106-233) — one fused call per branch
+    (row kernel + column kernel + reduction) returning both loss terms and d loss / d scores; the reference's
+    ~150 small tensor ops and per-video Python loops are gone, the order of its torch.randint draws is kept.
 The encoders stay PyTorch modules (model.py) so autograd carries the gradients from here into their parameters.
 """
-import math
-
 import numpy as np
 import torch
 
@@ -85,92 +83,53 @@ def kl_frame_loss(pred_curve, target_curve, mask, labels, temp=0.2):
     return _KLCurve.apply(pred_curve, target_curve.detach(), lens, temp)
 
 
-def clip_triplet_loss(scores, labels, margin, use_hard_negative, hard_pool_size):
-    """get_clip_triplet_loss (method/model.py:352-388) without the per-video Python loop.  The torch.randint
-    draws happen in the reference's order (one per video for v2t when not hard-negative, then one (M,) draw for
-    t2v), from the default CPU generator, so a seeded run samples the same negatives."""
-    M, N = scores.shape
-    dev = scores.device
-    lab = torch.as_tensor(np.asarray(labels), dtype=torch.long, device=dev)
-    onehot = torch.zeros((M, N), dtype=torch.bool, device=dev)
-    onehot[torch.arange(M, device=dev), lab] = True
-    # v2t: per video, mean of its positive queries vs one negative query
-    cnt = onehot.sum(dim=0)
-    pos_v = torch.where(onehot, scores, torch.zeros_like(scores)).sum(dim=0) / cnt      # nan for a video with no caption, like torch.mean of an empty slice
-    neg_sorted, _ = torch.sort(torch.where(onehot, torch.full_like(scores, -float("inf")), scores), dim=0,
-                               descending=True)                                          # (M, N): negatives first
+def negative_draws(labels, M, N, use_hard_negative, hard_pool_size):
+    """The negative-sampling draws of get_clip_triplet_loss (method/model.py:352-388) in the reference's order and
+    from the same (default CPU) generator: one torch.randint(0, n_neg) per video for the video -> text side unless
+    hard negatives are on (:363-368), then one (M,) torch.randint(1, max_idx) for the text -> video side (:376-380).
+    Returns (t2v_draw (M,), v2t_pick (N,)) int32 CPU tensors."""
     if use_hard_negative:
-        pick = torch.zeros((N,), dtype=torch.long, device=dev)
+        pick = torch.zeros((N,), dtype=torch.int64)
     else:
-        n_neg = (M - cnt).tolist()
-        pick = torch.cat([torch.randint(0, int(k), size=(1,)) for k in n_neg]).to(dev)
-    neg_v = neg_sorted.gather(0, pick[None, :])[0]
-    v2t_loss = (margin + neg_v - pos_v).clamp(min=0).sum()
-    # t2v: the positive video vs one of the top-ranked other videos
-    rows = torch.arange(M, device=dev)
-    pos_t = scores[rows, lab]
-    masked = scores.detach().clone()
-    masked[rows, lab] = 999
-    _, order = torch.sort(masked, descending=True, dim=1)
+        cnt = np.bincount(np.asarray(labels), minlength=N)
+        pick = torch.cat([torch.randint(0, int(M - c), size=(1,)) for c in cnt])
     max_idx = min(1 + hard_pool_size, N) if use_hard_negative else N
-    draw = torch.randint(1, max_idx, size=(M,)).to(dev)
-    neg_t = scores[rows, order[rows, draw]]
-    t2v_loss = (margin + neg_t - pos_t).clamp(min=0)
-    return t2v_loss.sum() / M + v2t_loss / N
+    draw = torch.randint(1, max_idx, size=(M,))
+    return draw.to(torch.int32), pick.to(torch.int32)
 
 
-def _label_matrix(labels, M, N, dev):
-    lab = torch.as_tensor(np.asarray(labels), dtype=torch.long, device=dev)
-    I = torch.zeros((M, N), device=dev)
-    I[torch.arange(M, device=dev), lab] = 1
-    return I, lab
+class _BranchLosses(torch.autograd.Function):
+    """(s_n, s_u, sims | None, labels, draws, config) -> (triplet, nce): value and gradient in one fused pass."""
+
+    @staticmethod
+    def forward(ctx, s_n, s_u, sims, labels, draw, pick, margin, soft, alpha, belta):
+        s_n, s_u = s_n.contiguous().float(), s_u.contiguous().float()
+        self_distil = sims is s_u or (sims is not None and sims.data_ptr() == s_u.data_ptr())
+        z = None
+        if soft:
+            z = s_u if self_distil else sims.contiguous().float()
+        terms, g_n, g_u = ops.train_losses(s_n, s_u, z, labels, draw, pick, margin, soft, alpha, belta)
+        ctx.save_for_backward(g_n, g_u)
+        return terms[0], terms[1]
+
+    @staticmethod
+    def backward(ctx, g_trip, g_nce):
+        g_n, g_u = ctx.saved_tensors
+        return g_trip * g_n, g_nce * g_u, None, None, None, None, None, None, None, None
 
 
-def clip_nce_loss(labels, scores):
-    """clip_nce (method/model_components.py:210-233), reduction 'mean'."""
-    M, N = scores.shape
-    I, lab = _label_matrix(labels, M, N, scores.device)
-    t2v_nom = scores[torch.arange(M, device=scores.device), lab]
-    t2v_den = torch.logsumexp(scores, dim=1)
-    present = I.sum(dim=0) > 0
-    v2t_nom = torch.logsumexp(scores.masked_fill((I == 0) & present[None, :], -float("inf")), dim=0)
-    v2t_den = torch.logsumexp(scores, dim=0)
-    zero = torch.zeros_like(v2t_den)
-    v2t = torch.where(present, v2t_den - torch.where(present, v2t_nom, zero), zero)   # absent videos stay 0 - 0
-    return torch.mean(t2v_den - t2v_nom) + torch.mean(v2t)
-
-
-def clip_nce_soft_loss(labels, scores, sims, alpha, belta):
-    """clip_nce_soft (method/model_components.py:106-208), reduction 'mean': hard part = first floor(alpha * bsz)
-    queries / videos with one-hot targets, soft part = the rest with targets blended with softmax(sims)."""
-    M, N = scores.shape
-    dev = scores.device
-    hardQ, hardV = math.floor(alpha * M), math.floor(alpha * N)
-    softQ, softV = M - hardQ, N - hardV
-    I, _ = _label_matrix(labels, M, N, dev)
-    rowsel = (torch.arange(M, device=dev) >= hardQ)[:, None]
-    I_Q = torch.where(rowsel, torch.clamp((1 - belta) * torch.softmax(sims, dim=-1) + belta * I, min=0), I)
-    vsel = (torch.arange(N, device=dev) >= hardV)[:, None]
-    I_V = torch.where(vsel, torch.clamp((1 - belta) * torch.softmax(sims.T, dim=-1) + belta * I.T, min=0), I.T)  # (N, M)
-    lse_rows = torch.logsumexp(scores, dim=1, keepdim=True)
-    t2v_nom_h = (I_Q[:hardQ] * scores[:hardQ]).sum()
-    t2v_den_h = (I_Q[:hardQ] * lse_rows[:hardQ]).sum()
-    t2v_nom_s = (I_Q[hardQ:] * scores[hardQ:]).sum()
-    t2v_den_s = (I_Q[hardQ:] * lse_rows[hardQ:]).sum()
-    present = I.sum(dim=0) > 0                                                   # videos in label_dict
-    v_nom = torch.logsumexp(torch.log(I_V + 1e-12) + scores.T, dim=1)            # (N,)
-    v_den = torch.logsumexp(scores, dim=0)
-    hard_v = present & (torch.arange(N, device=dev) < hardV)
-    soft_v = present & (torch.arange(N, device=dev) >= hardV)
-    zero = torch.zeros_like(v_nom)
-    v2t_nom_h, v2t_den_h = torch.where(hard_v, v_nom, zero).sum(), torch.where(hard_v, v_den, zero).sum()
-    v2t_nom_s, v2t_den_s = torch.where(soft_v, v_nom, zero).sum(), torch.where(soft_v, v_den, zero).sum()
-    hard_loss = soft_loss = 0.0
-    if hardQ != 0 and hardV != 0:
-        hard_loss = (t2v_den_h - t2v_nom_h) / hardQ + (v2t_den_h - v2t_nom_h) / hardV
-    if softQ != 0 and softV != 0:
-        soft_loss = (t2v_den_s - t2v_nom_s) / softQ + (v2t_den_s - v2t_nom_s) / softV
-    return alpha * hard_loss + (1 - alpha) * soft_loss
+def branch_losses(s_n, s_u, sims, labels, margin, use_hard_negative, hard_pool_size, soft, alpha, belta):
+    """Triplet loss on the cosine maxima + (soft) NCE loss on the raw maxima of one branch.  sims: the soft-target
+    source of clip_nce_soft — the teacher's raw maxima (no gradient), or s_u itself for the self-distilled
+    exploration branch (method/model.py:146-150); ignored when soft is False."""
+    M, N = s_n.shape
+    if soft and sims is not s_u and sims.requires_grad:
+        raise ValueError("branch_losses: soft targets from a separate tensor must not require grad")
+    draw, pick = negative_draws(labels, M, N, use_hard_negative, hard_pool_size)
+    lab = torch.as_tensor(np.asarray(labels), dtype=torch.int32)
+    dev = s_n.device
+    return _BranchLosses.apply(s_n, s_u, sims if soft else None, lab.to(dev), draw.to(dev), pick.to(dev), margin, soft,
+                               alpha, belta)
 
 
 def losses_from_encoded(model, enc, labels, mask):
@@ -182,19 +141,16 @@ def losses_from_encoded(model, enc, labels, mask):
     _, t_max_u, t_curve = in_batch_similarity(enc["teacher_q"], enc["teacher_ctx"], mask, labels)
     i_max_n, i_max_u, i_curve = in_batch_similarity(enc["inher_q"], enc["inher_ctx"], mask, labels)
     soft = cfg.label_style == "soft"
-    inher_trip = clip_triplet_loss(i_max_n, labels, cfg.margin, cfg.use_hard_negative, cfg.hard_pool_size)
-    if soft:
-        inher_nce = model.inher_nce_weight * clip_nce_soft_loss(labels, i_max_u, t_max_u, model.alpha, model.belta)
-    else:
-        inher_nce = model.inher_nce_weight * clip_nce_loss(labels, i_max_u)
+    hard, pool = cfg.use_hard_negative, cfg.hard_pool_size
+    inher_trip, nce = branch_losses(i_max_n, i_max_u, t_max_u, labels, cfg.margin, hard, pool, soft, model.alpha,
+                                    model.belta)
+    inher_nce = model.inher_nce_weight * nce
     explore_trip = explore_nce = 0
     if model.double_branch:
         e_max_n, e_max_u, _ = in_batch_similarity(enc["explore_q"], enc["explore_ctx"], mask, None)
-        explore_trip = clip_triplet_loss(e_max_n, labels, cfg.margin, cfg.use_hard_negative, cfg.hard_pool_size)
-        if soft:
-            explore_nce = model.explore_nce_weight * clip_nce_soft_loss(labels, e_max_u, e_max_u, model.alpha, model.belta)
-        else:
-            explore_nce = model.explore_nce_weight * clip_nce_loss(labels, e_max_u)
+        explore_trip, nce = branch_losses(e_max_n, e_max_u, e_max_u, labels, cfg.margin, hard, pool, soft,
+                                          model.alpha, model.belta)
+        explore_nce = model.explore_nce_weight * nce
     kl_intra = model.kl_intra_weight * model.weight * kl_frame_loss(i_curve, t_curve, mask, labels, 0.2)
     kl = kl_intra
     loss = inher_trip + inher_nce + kl + explore_trip + explore_nce

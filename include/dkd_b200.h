@@ -256,6 +256,27 @@ int dkd_train_sim_bwd(const float* q, const float* x, const float* rq, const flo
 int dkd_kl_curve_loss(const float* pred, const float* target, const int32_t* lens, int32_t M, int32_t L,
                       float temp, float* loss, float* dpred, void* stream);
 
+/* Fused triplet + NCE losses of one branch on the (M, N) in-batch score matrices, value and gradient together.
+ * Replaces get_clip_triplet_loss (method/model.py:352-388) on s_n (cosine maxima) and clip_nce / clip_nce_soft
+ * (method/model_components.py:106-233, reduction 'mean') on s_u (raw maxima):
+ *   labels (M)      positive video of each query;
+ *   t2v_draw (M)    position (>= 1) in the descending order of the query's row with the positive first — the
+ *                   torch.randint(1, max_idx) draw of :376-380 (1 = hardest negative);
+ *   v2t_pick (N)    rank (>= 0) among the video's negative queries, descending — 0 = hardest (:363-364), or the
+ *                   torch.randint(0, n_neg) draw of :366-368;
+ *   soft = 1        clip_nce_soft with soft targets from `sims` (teacher maxima, or s_u itself for the
+ *                   self-distilled exploration branch: the gradient through the targets is then included);
+ *   soft = 0        clip_nce (sims ignored).
+ * out_terms[0] = triplet loss, out_terms[1] = NCE loss (unweighted); g_n / g_u (M, N) = d out_terms[0] / d s_n and
+ * d out_terms[1] / d s_u.  workspace: dkd_train_losses_workspace_floats(M, N) floats.  Deterministic.
+ * N <= 2048, M <= 8192.
+ */
+int64_t dkd_train_losses_workspace_floats(int32_t M, int32_t N);
+int dkd_train_losses(const float* s_n, const float* s_u, const float* sims, const int32_t* labels,
+                     const int32_t* t2v_draw, const int32_t* v2t_pick, int32_t M, int32_t N, float margin,
+                     int32_t soft, float alpha, float belta, float* out_terms, float* g_n, float* g_u,
+                     float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,30 +80,41 @@ def test_kl_curve_loss_forward_and_backward(ops):
     assert (pc.grad.cpu() - 2.0 * pred.grad).abs().max() <= 1e-5
 
 
-@pytest.mark.parametrize("style,hard", [("soft", True), ("soft", False), ("hard", True)])
-def test_vectorised_losses_match_oracle_loops(ops, style, hard):
-    """train.py's loop-free triplet / NCE losses == the oracle's loop-for-loop restatement of the reference
-    (values and gradients; sampled negatives draw from the same seeded CPU generator in the same order)."""
+@pytest.mark.parametrize("style,hard,self_distil", [("soft", True, False), ("soft", False, False), ("hard", True, False),
+                                                    ("soft", True, True), ("soft", False, True)])
+@pytest.mark.parametrize("M,N,caps", [(640, 128, 5), (21, 7, 3), (9, 9, 1)])
+def test_fused_branch_losses_match_oracle_loops(ops, style, hard, self_distil, M, N, caps):
+    """The fused triplet + NCE kernel (value and gradient) == the oracle's loop-for-loop restatement of the
+    reference with autograd; sampled negatives draw from the same seeded CPU generator in the same order;
+    self_distil: the soft targets come from the scores themselves (exploration branch) and carry gradient."""
     from dkd_b200 import train
-    M, N = 640, 128
-    g = torch.Generator().manual_seed(11)
-    labels = [i // 5 for i in range(M)]
-    s = (0.2 * torch.randn(M, N, generator=g))
-    u = (3.0 * torch.randn(M, N, generator=g))
+    g = torch.Generator().manual_seed(11 + M)
+    labels = [i // caps for i in range(M)]
+    s = 0.2 * torch.randn(M, N, generator=g)
+    u = 3.0 * torch.randn(M, N, generator=g)
     sims = 3.0 * torch.randn(M, N, generator=g)
     sr, ur = s.clone().requires_grad_(True), u.clone().requires_grad_(True)
     torch.manual_seed(5)
-    ref = O.clip_triplet_loss(sr, labels, 0.1, hard, 20) + (O.clip_nce_soft(labels, ur, sims, 0.8, 0.8)
-                                                             if style == "soft" else O.clip_nce(labels, ur))
-    ref.backward()
+    trip_ref = O.clip_triplet_loss(sr, labels, 0.1, hard, 20)
+    nce_ref = (O.clip_nce_soft(labels, ur, ur if self_distil else sims, 0.8, 0.8) if style == "soft"
+               else O.clip_nce(labels, ur))
+    (trip_ref + 0.5 * nce_ref).backward()
     sc, uc = s.cuda().requires_grad_(True), u.cuda().requires_grad_(True)
     torch.manual_seed(5)
-    got = train.clip_triplet_loss(sc, labels, 0.1, hard, 20) + (train.clip_nce_soft_loss(labels, uc, sims.cuda(), 0.8, 0.8)
-                                                                 if style == "soft" else train.clip_nce_loss(labels, uc))
-    got.backward()
-    assert abs(float(got) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    trip, nce = train.branch_losses(sc, uc, uc if self_distil else sims.cuda(), labels, 0.1, hard, 20, style == "soft",
+                                    0.8, 0.8)
+    (trip + 0.5 * nce).backward()
+    assert abs(float(trip) - float(trip_ref)) <= 1e-5 * max(1.0, abs(float(trip_ref)))
+    assert abs(float(nce) - float(nce_ref)) <= 1e-5 * max(1.0, abs(float(nce_ref)))
     assert (sc.grad.cpu() - sr.grad).abs().max() <= 1e-6
     assert (uc.grad.cpu() - ur.grad).abs().max() <= 1e-6
+    # deterministic
+    sc2, uc2 = s.cuda().requires_grad_(True), u.cuda().requires_grad_(True)
+    torch.manual_seed(5)
+    t2, n2 = train.branch_losses(sc2, uc2, uc2 if self_distil else sims.cuda(), labels, 0.1, hard, 20, style == "soft",
+                                 0.8, 0.8)
+    (t2 + 0.5 * n2).backward()
+    assert torch.equal(sc2.grad, sc.grad) and torch.equal(uc2.grad, uc.grad) and float(t2) == float(trip)
 
 
 @pytest.mark.parametrize("tag", list(TRAIN_SETTINGS))

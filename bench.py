@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------
 def model_config(shape):
-    from oracle.ref_shim import model_config as mc, options
+    from dkd_b200.config import model_config as mc, options
     cfg = mc(shape["Dv"], shape["Dq"], hidden=shape["H"], n_heads=4, max_ctx_l=shape["L"], max_desc_l=shape["Lq"])
     return cfg, options()
 

@@ -249,24 +249,65 @@ def shard_range(Nv: int, rank_: int, world: int):
     return lo, min(lo + per, Nv)
 
 
-def merge_shards(local_scores, local_ids, group=None, merge_fn=None):
-    """All-gather every rank's per-query local top-K (NCCL over NVLink on the GPU box) and merge to
-    the global top-K with dkd_merge_topk.  merge_fn overrides the merge kernel (CPU gloo tests)."""
+def merge_shards(local_scores, local_ids, group=None, merge_fn=None, exchange="query_block", gather=True):
+    """Global per-query top-K from every rank's local top-K (NCCL over NVLink on the GPU box).
+
+    exchange="query_block" (default; SURVEY §8e's lower-volume alternative): one all-to-all hands rank r every
+    rank's lists for query block r (M/G queries), rank r merges only that block with dkd_merge_topk, and — when
+    `gather` — one all-gather of the merged blocks gives every rank the full (M, K) result.  Per rank that is
+    2 x M*K*8 bytes received and M/G merges instead of G x M*K*8 bytes and M merges for exchange="all_gather"
+    (every rank gathers every list and merges every query).  With gather=False the return value is
+    (scores, ids, (q_lo, q_hi)): the merged block this rank owns.
+    merge_fn overrides the merge kernel (CPU gloo tests)."""
     import torch.distributed as dist
     merge_fn = merge_fn or ops.merge_topk
     world = dist.get_world_size(group)
-    if world == 1:
-        return local_scores, local_ids
     M, K = local_scores.shape
-    gs = torch.empty((world, M, K), dtype=torch.float32, device=local_scores.device)
-    gi = torch.empty((world, M, K), dtype=torch.int32, device=local_scores.device)
+    if world == 1:
+        return (local_scores, local_ids) if gather else (local_scores, local_ids, (0, M))
+    dev = local_scores.device
+    if exchange == "all_gather":
+        gs = torch.empty((world, M, K), dtype=torch.float32, device=dev)
+        gi = torch.empty((world, M, K), dtype=torch.int32, device=dev)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
+            dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
+        else:  # gloo (CPU tests): list form
+            dist.all_gather(list(gs.unbind(0)), local_scores.contiguous(), group=group)
+            dist.all_gather(list(gi.unbind(0)), local_ids.contiguous(), group=group)
+        ms, mi = merge_fn(gs, gi)
+        return (ms, mi) if gather else (ms, mi, (0, M))
+    if exchange != "query_block":
+        raise ValueError("exchange must be 'query_block' or 'all_gather'")
+    rank_ = dist.get_rank(group)
+    Mb = (M + world - 1) // world
+    # (score bits, id) packed per destination: send[g] = my lists for query block g, padded with (-inf, -1)
+    send = torch.empty((world, 2, Mb, K), dtype=torch.int32, device=dev)
+    pad = world * Mb - M
+    sc = local_scores.contiguous().view(torch.int32)
+    if pad:
+        neg_inf = torch.full((pad, K), float("-inf"), dtype=torch.float32, device=dev).view(torch.int32)
+        sc = torch.cat([sc, neg_inf])
+        ids = torch.cat([local_ids, torch.full((pad, K), -1, dtype=torch.int32, device=dev)])
+    else:
+        ids = local_ids
+    send[:, 0] = sc.view(world, Mb, K)
+    send[:, 1] = ids.view(world, Mb, K)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    bs, bi = merge_fn(recv[:, 0].contiguous().view(torch.float32), recv[:, 1].contiguous())      # (Mb, K): my block
+    q_lo, q_hi = min(rank_ * Mb, M), min((rank_ + 1) * Mb, M)
+    if not gather:
+        return bs[: q_hi - q_lo], bi[: q_hi - q_lo], (q_lo, q_hi)
+    mine = torch.stack([bs.contiguous().view(torch.int32), bi])                                     # (2, Mb, K)
+    full = torch.empty((world, 2, Mb, K), dtype=torch.int32, device=dev)
     if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
-        dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
-    else:  # gloo (CPU tests): list form
-        dist.all_gather(list(gs.unbind(0)), local_scores.contiguous(), group=group)
-        dist.all_gather(list(gi.unbind(0)), local_ids.contiguous(), group=group)
-    return merge_fn(gs, gi)
+        dist.all_gather_into_tensor(full, mine, group=group)
+    else:
+        dist.all_gather(list(full.unbind(0)), mine, group=group)
+    ms = full[:, 0].reshape(world * Mb, K)[:M].contiguous().view(torch.float32)
+    mi = full[:, 1].reshape(world * Mb, K)[:M].contiguous()
+    return ms, mi
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """CPU, world_size 2 over gloo: the host side of the multi-GPU path — contiguous video
-shards, local top-K with global ids, all-gather, merge — gives the same top-K as one unsharded corpus.
+shards, local top-K with global ids, exchange (all-to-all by query block + all-gather of the merged blocks, or one
+all-gather of every list), merge — gives the same top-K as one unsharded corpus.
 The merge kernel itself (dkd_merge_topk) is GPU-only and is checked in tests/test_gpu_kernels.py; here
 `merge_fn` is a numpy stand-in with the same (score desc, id asc) order."""
 import os
@@ -47,7 +48,7 @@ def _np_merge(gs, gi):
     return torch.from_numpy(out_s), torch.from_numpy(out_i)
 
 
-def _worker(rank, world, port, Nv, M, K, q):
+def _worker(rank, world, port, Nv, M, K, q, exchange="query_block"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -59,21 +60,26 @@ def _worker(rank, world, port, Nv, M, K, q):
         scores[:, 3::7] = 0.5                       # exact ties across shards: lower global id must win
         lo, hi = engine.shard_range(Nv, rank, world)
         ls, li = _np_topk(scores[:, lo:hi].numpy(), K, lo)
-        ms, mi = engine.merge_shards(ls, li, merge_fn=_np_merge)
+        ms, mi = engine.merge_shards(ls, li, merge_fn=_np_merge, exchange=exchange)
         ref = O.topk_ids(scores.numpy(), K)
         kk = min(K, Nv)
         ok = np.array_equal(mi.numpy()[:, :kk], ref[:, :kk]) and np.array_equal(
             ms.numpy()[:, :kk], np.take_along_axis(scores.numpy(), ref[:, :kk], 1))
+        if exchange == "query_block":       # the un-gathered form: this rank's query block only
+            bs, bi, (q_lo, q_hi) = engine.merge_shards(ls, li, merge_fn=_np_merge, gather=False)
+            ok = ok and np.array_equal(bi.numpy(), mi.numpy()[q_lo:q_hi]) and np.array_equal(
+                bs.numpy(), ms.numpy()[q_lo:q_hi]) and (q_lo, q_hi) == ((M + world - 1) // world * rank,
+                                                                      min((M + world - 1) // world * (rank + 1), M))
         q.put((rank, bool(ok), (lo, hi)))
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, Nv, M, K):
+def _run(world, Nv, M, K, exchange="query_block"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, Nv, M, K, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, Nv, M, K, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
@@ -87,6 +93,18 @@ def test_sharded_merge_world2_equals_global_topk():
     res = _run(2, Nv=501, M=37, K=100)
     assert all(ok for _, ok, _ in res)
     assert [r[2] for r in res] == [(0, 251), (251, 501)]
+
+
+def test_sharded_merge_world2_all_gather_exchange():
+    """The all-gather form (every rank gathers every list) gives the same result as the query-block exchange."""
+    res = _run(2, Nv=501, M=37, K=100, exchange="all_gather")
+    assert all(ok for _, ok, _ in res)
+
+
+def test_sharded_merge_world3_ragged_query_blocks():
+    """3 ranks, 37 queries: blocks of 13 / 13 / 11 queries (the last one padded on the wire)."""
+    res = _run(3, Nv=200, M=37, K=100)
+    assert all(ok for _, ok, _ in res)
 
 
 def test_sharded_merge_world2_small_shards_pad():

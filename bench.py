@@ -554,7 +554,11 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
-                "parity": parity}
+                "parity": parity,
+                "certify": {"eps": engine.CERT_EPS, "checked_queries": engine.STATS["certify_checked_queries"],
+                            "fallback_queries": engine.STATS["certify_fallback_queries"],
+                            "note": "queries whose exact 100th score is within eps of the last candidate's approximate "
+                                    "score are re-ranked by the all-exact path (all calls of this process)"}}
         if not args.no_cpu_baseline and world >= 1:
             nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
             line["cpu_baseline"] = run_cpu_baseline(cpu_shape, args.workload, nq)

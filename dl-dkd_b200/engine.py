@@ -203,13 +203,22 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
     return fused, per
 
 
+CERT_EPS = 1.0e-3   # bound on |approximate fused score - exact fused score| (north_star tolerance; asserted on dense
+                    # scores by tests/test_gpu_kernels.py / test_gpu_dropin.py)
+STATS = {"certify_fallback_queries": 0, "certify_checked_queries": 0}
+
+
 def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", precision="bf16", rescore=True,
-         Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU):
+         Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU, certify=True):
     """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score.
 
     precision="bf16" + rescore: bf16 GEMM scores pick Kc >= K candidates per query, the exact fp32
-    kernels re-score them, the K best survive — identical to precision="exact" unless the true
-    top-K leaks out of the approximate top-Kc (bounded by the 1e-3 bf16 error).
+    kernels re-score them, the K best survive.  certify: a query's list is accepted only if its exact K-th
+    score exceeds the approximate score of the last candidate by more than CERT_EPS — every non-candidate
+    scores at most that approximate value, so (approximation error <= CERT_EPS) none of them can belong in the
+    top-K.  The few queries that fail the check are re-ranked by the all-exact path, which makes the result equal
+    to precision="exact" for every query instead of "for every query we tested" (one scalar device->host read per
+    call; STATS counts the fallbacks).
     """
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
@@ -225,7 +234,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     if precision == "exact" or not rescore:
         return ops.topk(fused, K, pc.id_base)
     Kc = max(Kc, K)
-    _, cand = ops.topk(fused, Kc, pc.id_base)
+    approx_s, cand = ops.topk(fused, Kc, pc.id_base)
     csr = ops.candidates_to_csr(cand, pc.Nv, pc.id_base)
     cand_scores = torch.full((pq.M, Kc), float("-inf"), dtype=torch.float32, device=cand.device)
     if head == "frame":
@@ -239,7 +248,20 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2])
             wb = wbs[bi] if nb == 2 else 1.0
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
-    return ops.sort_candidates(cand_scores, cand, K)
+    out_s, out_i = ops.sort_candidates(cand_scores, cand, K)
+    if certify and Kc < pc.Nv:
+        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + CERT_EPS
+        n_unsure = int(unsure.sum())
+        STATS["certify_checked_queries"] += pq.M
+        STATS["certify_fallback_queries"] += n_unsure
+        if n_unsure:
+            idx = unsure.nonzero().squeeze(1)
+            sub = PreparedQueries(M=n_unsure, Mpad=ops.round_up(n_unsure, 256), qn=[q[idx].contiguous() for q in pq.qn],
+                                  qb=[None] * nb, qh=[None] * nb)
+            es, ei = rank(pc, sub, K=K, head=head, precision="exact", w_clip=w_clip, w_frame=w_frame)
+            out_s[idx] = es
+            out_i[idx] = ei
+    return out_s, out_i
 
 
 def shard_range(Nv: int, rank_: int, world: int):

@@ -312,6 +312,10 @@ def main():
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
+    ap.add_argument("--operand", default="bf16", choices=["bf16", "fp16"],
+                    help="GEMM operand type: bf16 (north_star, default) or IEEE half (reported variant: same tensor "
+                         "rate and bytes, 8 x smaller rounding error -> 8 x fewer ambiguous pairs)")
+    ap.add_argument("--candidates", type=int, default=K_CAND)
     ap.add_argument("--e2e-steps", type=int, default=None, help="timed steps of the e2e leg (default max(3, steps/2))")
     args = ap.parse_args()
     if args.impl == "dkd_b200" and not args.profile:
@@ -393,10 +397,10 @@ def main():
         torch.cuda.synchronize()
         prep_ms, pc = None, None
 
-        def step(q_dev, precision="bf16"):
+        def step(q_dev, precision=args.operand):
             pqs = engine.split_queries(q_dev, args.query_batch)
             chunks = engine.iter_chunks(frames, mask, args.chunk_videos, id_base=rank * Nv)
-            s, i = engine.rank_streamed(chunks, pqs, attn, K=K_TOP, T=shape["T"], precision=precision, Kc=K_CAND)
+            s, i = engine.rank_streamed(chunks, pqs, attn, K=K_TOP, T=shape["T"], precision=precision, Kc=args.candidates)
             if world > 1:
                 s, i = engine.merge_shards(s, i)
             return s, i
@@ -406,16 +410,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
-                                   T=shape["T"], heads=(head,), id_base=rank * shape["Nv"])
+                                   T=shape["T"], heads=(head,), precisions=("exact", args.operand),
+                                   id_base=rank * shape["Nv"])
         e1.record()
         torch.cuda.synchronize()
         prep_ms = e0.elapsed_time(e1)
         del frames
         qs = [q.contiguous() for q in qs]
 
-        def step(q_dev, precision="bf16"):
+        def step(q_dev, precision=args.operand):
             pq = engine.prepare_queries(q_dev)
-            s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision=precision, rescore=True, Kc=K_CAND)
+            s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision=precision, rescore=True, Kc=args.candidates)
             if world > 1:
                 s, i = engine.merge_shards(s, i)
             return s, i
@@ -436,7 +441,8 @@ def main():
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.set_timed({"dkd_score_max_bf16"})
+    gemm_entry = "dkd_score_max_f16" if args.operand == "fp16" else "dkd_score_max_bf16"
+    _lib.set_timed({gemm_entry})
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     ev[0].record()
@@ -446,7 +452,7 @@ def main():
     barrier()
     clocks = sampler.result()
     ms_total = ev[0].elapsed_time(ev[1])
-    gemm_ms = _lib.timed_results().get("dkd_score_max_bf16", [])
+    gemm_ms = _lib.timed_results().get(gemm_entry, [])
     _lib.set_timed(set())
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -538,7 +544,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload)
-        roofline = {"bound": "tensor", "kernel": "score_max_bf16_kernel (tcgen05 GEMM + fused max/argmax)",
+        roofline = {"bound": "tensor", "kernel": "score_max_bf16_kernel (tcgen05 GEMM + fused max/argmax)" +
+                                                   (" on IEEE-half operands" if args.operand == "fp16" else ""),
                     "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
                     "frac": achieved / pk["bf16_burst"] if achieved else None,
                     "frac_of_sustained_peak": achieved / pk["bf16_sustained"] if achieved else None,
@@ -548,9 +555,10 @@ def main():
                     "traffic": traffic}
         line = {"metric": "query-video pairs scored+ranked/sec", "value": value, "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.operand == "bf16" else "f16",
                 "data": "synthetic", "config": dict(cfg_common, parallelism=f"video-shard x{world}",
-                                                    candidates=K_CAND, rescoring="exact fp32"),
+                                                    candidates=args.candidates, rescoring="exact fp32"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),

@@ -84,7 +84,7 @@ __global__ void downsample_clips_kernel(const float* __restrict__ frames,
 // division instead of 4 per feature pair (the IEEE divisions made the first version issue bound at
 // 1.7 TB/s).  kMeans = true also writes the un-normalised fp32 means with the exact sum / w division
 // (tests, small shapes).
-template <int kPairs, bool kMeans>  // D = 64 * kPairs
+template <int kPairs, bool kMeans, bool kHalf = false>  // D = 64 * kPairs; kHalf: rows as IEEE half instead of bf16
 __global__ void __launch_bounds__(512)
 build_proposals_kernel(const float* __restrict__ clips, int T, int D,
                        __nv_bfloat16* __restrict__ prop_bf16, float* __restrict__ prop_scale,
@@ -132,8 +132,12 @@ build_proposals_kernel(const float* __restrict__ clips, int T, int D,
               make_float2(__fdiv_rn(acc[2 * j], fw), __fdiv_rn(acc[2 * j + 1], fw));
         }
         if (prop_bf16) {
-          __nv_bfloat162 b = __floats2bfloat162_rn(__fmul_rn(acc[2 * j], scale), __fmul_rn(acc[2 * j + 1], scale));
-          *reinterpret_cast<__nv_bfloat162*>(&prop_bf16[ro + 64 * j + 2 * lane]) = b;
+          const float a = __fmul_rn(acc[2 * j], scale), b = __fmul_rn(acc[2 * j + 1], scale);
+          if (kHalf) {
+            *reinterpret_cast<__half2*>(&prop_bf16[ro + 64 * j + 2 * lane]) = __floats2half2_rn(a, b);
+          } else {
+            *reinterpret_cast<__nv_bfloat162*>(&prop_bf16[ro + 64 * j + 2 * lane]) = __floats2bfloat162_rn(a, b);
+          }
         }
       }
     }
@@ -482,10 +486,15 @@ extern "C" int dkd_downsample_clips(const float* frames, const int32_t* lengths,
 
 template <int kPairs>
 static int launch_build_proposals(const float* clips, int Nv, int T, int D, uint16_t* pb, float* ps,
-                                  float* pf, cudaStream_t st) {
+                                  float* pf, cudaStream_t st, bool half) {
   size_t smem = (size_t)T * D * sizeof(float);
   auto* bf = reinterpret_cast<__nv_bfloat16*>(pb);
-  if (pf) {
+  if (half) {
+    if (pf) return DKD_ERR_ARG;
+    DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_proposals_kernel<kPairs, false, true><<<Nv, 512, smem, st>>>(clips, T, D, bf, ps, pf);
+  } else if (pf) {
     DKD_CUDA_TRY(cudaFuncSetAttribute(build_proposals_kernel<kPairs, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     build_proposals_kernel<kPairs, true><<<Nv, 512, smem, st>>>(clips, T, D, bf, ps, pf);
@@ -498,24 +507,35 @@ static int launch_build_proposals(const float* clips, int Nv, int T, int D, uint
   return DKD_OK;
 }
 
-extern "C" int dkd_build_proposals(const float* clips, int32_t Nv, int32_t T, int32_t D,
-                                   uint16_t* prop_bf16, float* prop_scale, float* prop_f32,
-                                   void* stream) {
+static int build_proposals_any(const float* clips, int32_t Nv, int32_t T, int32_t D, uint16_t* prop_rows,
+                               float* prop_scale, float* prop_f32, void* stream, bool half) {
   if (!clips || Nv < 0 || T <= 0 || D <= 0) return DKD_ERR_ARG;
   if (T > 32 || D % 64 != 0 || D > 512) return DKD_ERR_SHAPE;
   if (Nv == 0) return DKD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (D / 64) {
-    case 1: return launch_build_proposals<1>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 2: return launch_build_proposals<2>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 3: return launch_build_proposals<3>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 4: return launch_build_proposals<4>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 5: return launch_build_proposals<5>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 6: return launch_build_proposals<6>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 7: return launch_build_proposals<7>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
-    case 8: return launch_build_proposals<8>(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, st);
+    case 1: return launch_build_proposals<1>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 2: return launch_build_proposals<2>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 3: return launch_build_proposals<3>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 4: return launch_build_proposals<4>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 5: return launch_build_proposals<5>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 6: return launch_build_proposals<6>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 7: return launch_build_proposals<7>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
+    case 8: return launch_build_proposals<8>(clips, Nv, T, D, prop_rows, prop_scale, prop_f32, st, half);
   }
   return DKD_ERR_SHAPE;
+}
+
+extern "C" int dkd_build_proposals(const float* clips, int32_t Nv, int32_t T, int32_t D,
+                                   uint16_t* prop_bf16, float* prop_scale, float* prop_f32,
+                                   void* stream) {
+  return build_proposals_any(clips, Nv, T, D, prop_bf16, prop_scale, prop_f32, stream, false);
+}
+
+extern "C" int dkd_build_proposals_f16(const float* clips, int32_t Nv, int32_t T, int32_t D,
+                                       uint16_t* prop_f16, float* prop_scale, void* stream) {
+  if (!prop_f16) return DKD_ERR_ARG;
+  return build_proposals_any(clips, Nv, T, D, prop_f16, prop_scale, nullptr, stream, true);
 }
 
 template <int kChunks>

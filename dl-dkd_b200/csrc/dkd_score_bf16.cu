@@ -64,9 +64,10 @@ __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, 
   if (t.best != before) t.chunk = cid;
 }
 
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__host__ __device__ __forceinline__ uint32_t make_idesc(int n, int m) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16 (format 1) or IEEE half (format 0), both K-major, M=m, N=n.
+__host__ __device__ __forceinline__ uint32_t make_idesc(int n, int m, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct GemmParams {
@@ -82,6 +83,7 @@ struct GemmParams {
   uint32_t* out_flags; // optional: bit (n & 31) of word [m][n >> 5] set when that gap is below `tau`
   float tau;
   int flag_words;     // words per query row = ceil(Nv / 32)
+  int f16;            // operands are IEEE half instead of bf16 (same 2-byte layout, same MMA kind::f16 rate)
   int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0,
                       // 4 = MMA does not wait for the corpus ring, 8 = no corpus TMA at all (timing experiments)
   int64_t ld_out;
@@ -209,7 +211,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // The issue path is the critical resource of this kernel (the tensor pipe only queues a few MMAs),
       // so descriptors are built once and advanced with 32-bit immediates, and the wait for the NEXT ring
       // stage is taken while half of the current stage's MMAs are still queued.
-      const uint32_t idesc = make_idesc(p.block_n, kBlockM * kCta);
+      const uint32_t idesc = make_idesc(p.block_n, kBlockM * kCta, p.f16 != 0);
       const bool elected = elect_one();
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a));
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b));
@@ -385,14 +387,15 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       bool f16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return DKD_ERR_DRIVER;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? DKD_OK : DKD_ERR_DRIVER;
@@ -430,10 +433,10 @@ static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const
   return DKD_OK;
 }
 
-extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
-                                  int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
-                                  int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
-                                  float tau, void* stream) {
+static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
+                        int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                        int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
+                        float tau, void* stream, bool f16) {
   if (!q_bf16 || !x_bf16 || !out_max || M < 0 || Nv < 0 || ld_out < Nv) return DKD_ERR_ARG;
   if (Mpad < M || Mpad % kBlockM != 0) return DKD_ERR_SHAPE;
   if (R <= 0 || R > 4096 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
@@ -470,13 +473,14 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
   const size_t smem_bytes = fixed + (size_t)stages * b_stage;
 
   CUtensorMap map_q, map_x;
-  int rc = make_map_2d(&map_q, q_bf16, (uint64_t)Mpad, (uint64_t)D, kBlockM);
+  int rc = make_map_2d(&map_q, q_bf16, (uint64_t)Mpad, (uint64_t)D, kBlockM, f16);
   if (rc) return rc;
-  rc = make_map_2d(&map_x, x_bf16, (uint64_t)Nv * R, (uint64_t)D, (uint32_t)(block_n / cta));
+  rc = make_map_2d(&map_x, x_bf16, (uint64_t)Nv * R, (uint64_t)D, (uint32_t)(block_n / cta), f16);
   if (rc) return rc;
 
   GemmParams p{};
   p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
+  p.f16 = f16 ? 1 : 0;
   { const char* e = getenv("DKD_GEMM_DEBUG"); p.debug_flags = e ? atoi(e) : 0; }
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
@@ -494,4 +498,20 @@ extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpa
                             : launch_gemm<false, 2>(map_q, map_x, p, grid, smem_bytes, st);
   return mask ? launch_gemm<true, 1>(map_q, map_x, p, grid, smem_bytes, st)
               : launch_gemm<false, 1>(map_q, map_x, p, grid, smem_bytes, st);
+}
+
+extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
+                                  int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                                  int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
+                                  float tau, void* stream) {
+  return score_max_tc(q_bf16, M, Mpad, x_bf16, Nv, R, D, mask, out_max, out_arg, out_gap, ld_out, out_flags, tau,
+                      stream, false);
+}
+
+extern "C" int dkd_score_max_f16(const uint16_t* q_f16, int32_t M, int32_t Mpad, const uint16_t* x_f16,
+                                 int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                                 int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
+                                 float tau, void* stream) {
+  return score_max_tc(q_f16, M, Mpad, x_f16, Nv, R, D, mask, out_max, out_arg, out_gap, ld_out, out_flags, tau,
+                      stream, true);
 }

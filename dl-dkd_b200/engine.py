@@ -43,6 +43,8 @@ class BranchData:
     clip_planes: Optional[torch.Tensor] = None
     prop_scale: Optional[torch.Tensor] = None
     prop_b: Optional[torch.Tensor] = None
+    prop_h: Optional[torch.Tensor] = None       # IEEE-half proposals: GEMM B operand of precision="fp16"
+    frames_h: Optional[torch.Tensor] = None     # IEEE-half frames: frame head, precision="fp16"
     table_f: Optional[torch.Tensor] = None
     table_h: Optional[torch.Tensor] = None
 
@@ -94,10 +96,13 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
         fr = fr.contiguous().float()
         bd = BranchData()
         if "frame" in heads:
-            fn, fb = ops.normalize_rows(fr, want_f32="exact" in precisions or "bf16" in precisions,
-                                        want_bf16="bf16" in precisions)
+            approx = "bf16" in precisions or "fp16" in precisions
+            out = ops.normalize_rows(fr, want_f32="exact" in precisions or approx,
+                                     want_bf16="bf16" in precisions, want_f16="fp16" in precisions)
+            fn, fb, fh = out if len(out) == 3 else (out[0], out[1], None)
             bd.frames_n = None if fn is None else fn.view(Nv, L, D)
             bd.frames_b = fb
+            bd.frames_h = fh
             if bd.frames_n is not None and D % 32 == 0:
                 bd.frame_planes = ops.pack_rows(bd.frames_n)
         if "two_scale" in heads:
@@ -109,11 +114,13 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
             pb, ps, _ = ops.build_proposals(bd.clips, want_bf16="bf16" in precisions, want_scale=True)
             bd.prop_b = None if pb is None else pb.view(-1, D)
             bd.prop_scale = ps
+            if "fp16" in precisions:
+                bd.prop_h = ops.build_proposals_f16(bd.clips)[0].view(-1, D)
             # W_k / W_v projections: plain library GEMMs in corpus preparation
             key = F.linear(fr, kw, kb).contiguous()
             val = F.linear(fr, vw, vb).contiguous()
             bd.table_f, bd.table_h = ops.frame_attn_table(key, val, bd.clips, lengths, want_f32=True,
-                                                          want_f16="bf16" in precisions)
+                                                          want_f16="bf16" in precisions or "fp16" in precisions)
             del key, val
         pc.branches.append(bd)
     return pc
@@ -160,9 +167,11 @@ def _exact_rows(bd: BranchData, qn, pc: PreparedCorpus, csr=None):
 def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", want_arg=False):
     """Per-branch dense (M, Nv) scores of the reference head. Returns list of (scores, argmax)."""
     out = []
-    for bd, qn, qb in zip(pc.branches, pq.qn, pq.qb):
+    for bd, qn, qb, qh in zip(pc.branches, pq.qn, pq.qb, pq.qh):
         if precision == "exact":
             s, a = _exact_rows(bd, qn, pc)
+        elif precision == "fp16":
+            s, a = ops.score_max_bf16(qh, pq.M, bd.frames_h, pc.Nv, pc.L, pc.mask_u8)
         else:
             s, a = ops.score_max_bf16(qb, pq.M, bd.frames_b, pc.Nv, pc.L, pc.mask_u8)
         out.append((s, a))
@@ -170,10 +179,13 @@ def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact",
 
 
 AMBIGUITY_TAU = 1.0e-3  # bf16 argmax gaps below this are re-resolved in fp32 (DESIGN.md "bf16 and the key clip")
+# precision="fp16": IEEE-half GEMM operands have 11 significant bits instead of 8 — every operand-rounding bound
+# shrinks by 8: ambiguity threshold, and the dense-score error bound behind the candidate certificate
+AMBIGUITY_TAU_F16 = AMBIGUITY_TAU / 8
 
 
 def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact", w_clip=0.7, w_frame=0.3,
-                         want_frame=False, tau=AMBIGUITY_TAU):
+                         want_frame=False, tau=None):
     """Returns (fused (M, Nv), per-branch list of dict(clip, key_clip, frame|None)).
 
     precision="bf16": the tcgen05 GEMM also flags (one bit per pair) the (query, video) pairs whose gap between
@@ -184,17 +196,23 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
     wbs = _branch_weights(nb)
     fused = None
     per = []
+    if tau is None:
+        tau = AMBIGUITY_TAU_F16 if precision == "fp16" else AMBIGUITY_TAU
     for bi, (bd, qn, qb, qh) in enumerate(zip(pc.branches, pq.qn, pq.qb, pq.qh)):
         if precision == "exact":
             s_clip, k_clip = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale)
             q, tab = qn, bd.table_f
         else:
+            if precision == "fp16":
+                qb, prop = qh, bd.prop_h
+            else:
+                prop = bd.prop_b
             if tau > 0:
-                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P, flag_tau=tau)
+                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.P, flag_tau=tau)
                 vb, ql, vc, slot = ops.select_flagged(flags, pc.Nv)
                 ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=(vb, ql, vc), scatter=(slot, s_clip, k_clip))
             else:
-                s_clip, k_clip = ops.score_max_bf16(qb, pq.M, bd.prop_b, pc.Nv, pc.P)
+                s_clip, k_clip = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.P)
             q, tab = qh, bd.table_h
         wb = wbs[bi] if nb == 2 else 1.0
         fused, fr = ops.frame_fuse(q, tab, s_clip, k_clip, w_clip, w_frame, wb, fused=fused, accumulate=bi > 0,
@@ -204,12 +222,13 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
 
 
 CERT_EPS = 1.0e-3   # bound on |approximate fused score - exact fused score| (north_star tolerance; asserted on dense
-                    # scores by tests/test_gpu_kernels.py / test_gpu_dropin.py)
+                    # scores at full size by tests/test_gpu_configs.py::test_config_dense_error_within_certificate_eps)
+CERT_EPS_F16 = 2.5e-4
 STATS = {"certify_fallback_queries": 0, "certify_checked_queries": 0}
 
 
 def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", precision="bf16", rescore=True,
-         Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU, certify=True):
+         Kc=128, w_clip=0.7, w_frame=0.3, tau=None, certify=True):
     """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score.
 
     precision="bf16" + rescore: bf16 GEMM scores pick Kc >= K candidates per query, the exact fp32
@@ -250,7 +269,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
     out_s, out_i = ops.sort_candidates(cand_scores, cand, K)
     if certify and Kc < pc.Nv:
-        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + CERT_EPS
+        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + (CERT_EPS_F16 if precision == "fp16" else CERT_EPS)
         n_unsure = int(unsure.sum())
         STATS["certify_checked_queries"] += pq.M
         STATS["certify_fallback_queries"] += n_unsure
@@ -354,7 +373,7 @@ def iter_chunks(frames_by_branch, mask, chunk_videos=8192, id_base=0):
 
 
 def rank_streamed(chunks, pqs, attn_params=None, K=100, T=ops.T_CLIPS, head="two_scale", precision="bf16",
-                  rescore=True, Kc=128, w_clip=0.7, w_frame=0.3, tau=AMBIGUITY_TAU):
+                  rescore=True, Kc=128, w_clip=0.7, w_frame=0.3, tau=None):
     """Per-query top-K over a corpus presented as successive chunks of videos.
 
     chunks: iterable of (frames_by_branch, mask, id_base) — e.g. iter_chunks() over a resident shard, or a
@@ -363,7 +382,7 @@ def rank_streamed(chunks, pqs, attn_params=None, K=100, T=ops.T_CLIPS, head="two
     (query, video) score is produced by the same kernels on the same rows and the ordering (score desc, id asc)
     is total, so a merge of per-chunk top-K lists is the global top-K."""
     running = [None] * len(pqs)
-    precisions = ("exact", "bf16") if precision == "bf16" else ("exact",)
+    precisions = ("exact", precision) if precision != "exact" else ("exact",)
     for frames, mask, id_base in chunks:
         pc = prepare_corpus(frames, mask, attn_params, T=T, heads=(head,), precisions=precisions, id_base=id_base)
         for b, pq in enumerate(pqs):

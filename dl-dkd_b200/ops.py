@@ -65,6 +65,17 @@ def downsample_clips(frames, lengths, T=T_CLIPS):
     return clips
 
 
+def build_proposals_f16(clips, want_scale=False):
+    """(Nv, T, D) clips -> (prop_f16 (Nv,P,D) normalised IEEE-half rows, prop_scale (Nv,P) | None)."""
+    _chk(clips, torch.float32, "clips")
+    Nv, T, D = clips.shape
+    P = num_proposals(T)
+    ph = torch.empty((Nv, P, D), dtype=torch.float16, device=clips.device)
+    ps = torch.empty((Nv, P), dtype=torch.float32, device=clips.device) if want_scale else None
+    _lib.call("dkd_build_proposals_f16", _p(clips), Nv, T, D, _p(ph), _p(ps), _stream())
+    return ph, ps
+
+
 def build_proposals(clips, want_bf16=True, want_scale=True, want_f32=False):
     """(Nv, T, D) clips -> (prop_bf16 (Nv,P,D) normalised, prop_scale (Nv,P), prop_f32 (Nv,P,D) means)."""
     _chk(clips, torch.float32, "clips")
@@ -195,9 +206,10 @@ def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
 def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=None, want_gap=False, flag_tau=None):
     """tcgen05 GEMM + fused max/argmax: q_bf16 (Mpad,D), x_bf16 (Nv*R, D) -> (max (M,Nv), argmax (M,Nv))
     [+ gap (M,Nv) = best - runner-up when want_gap] [+ flags (M, ceil(Nv/32)) uint32 bit matrix of the pairs
-    whose gap is below flag_tau]."""
-    _chk(q_bf16, torch.bfloat16, "q_bf16")
-    _chk(x_bf16, torch.bfloat16, "x_bf16")
+    whose gap is below flag_tau].  Both operands bf16, or both IEEE half (dkd_score_max_f16)."""
+    half = isinstance(q_bf16, torch.Tensor) and q_bf16.dtype == torch.float16
+    _chk(q_bf16, torch.float16 if half else torch.bfloat16, "q_bf16")
+    _chk(x_bf16, torch.float16 if half else torch.bfloat16, "x_bf16")
     Mpad, D = q_bf16.shape
     if x_bf16.numel() != Nv * R * D:
         raise _lib.DkdError("x_bf16 does not hold Nv*R rows of D features")
@@ -208,7 +220,8 @@ def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=No
     oa = out_arg if out_arg is not None else torch.empty((M, Nv), dtype=torch.int32, device=dev)
     og = torch.empty((M, Nv), dtype=torch.float32, device=dev) if want_gap else None
     fl = torch.zeros((M, (Nv + 31) // 32), dtype=torch.int32, device=dev) if flag_tau is not None else None
-    _lib.call("dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D, _p(mask), _p(om), _p(oa), _p(og), Nv,
+    _lib.call("dkd_score_max_f16" if half else "dkd_score_max_bf16", _p(q_bf16), M, Mpad, _p(x_bf16), Nv, R, D,
+              _p(mask), _p(om), _p(oa), _p(og), Nv,
               _p(fl), float(flag_tau or 0.0), _stream())
     out = (om, oa)
     if want_gap:

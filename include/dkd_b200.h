@@ -140,6 +140,17 @@ int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const ui
                        int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags, float tau,
                        void* stream);
 
+/* The same kernel on IEEE-half operands (kind::f16 with the f16 formats: same tensor rate and bytes as bf16, 11
+ * instead of 8 significant bits — operand rounding error 8 x smaller; values are L2-normalised, so the narrower
+ * exponent range costs nothing).  A reported variant: north_star specifies bf16, which stays the default. */
+int dkd_score_max_f16(const uint16_t* q_f16, int32_t M, int32_t Mpad, const uint16_t* x_f16,
+                      int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
+                      int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags, float tau,
+                      void* stream);
+/* dkd_build_proposals with IEEE-half rows (B operand of dkd_score_max_f16). */
+int dkd_build_proposals_f16(const float* clips, int32_t Nv, int32_t T, int32_t D, uint16_t* prop_f16,
+                            float* prop_scale, void* stream);
+
 /* Per-video lists of the flagged pairs of a dkd_score_max_bf16 bit matrix: video n owns entries
  * [vid_begin[n], vid_begin[n] + vid_cnt[n]) of q_list (query index) / slot (m * ld + n), in any order; runs
  * are placed by a global cursor (1 int scratch).  One pass over the bit matrix, one block per 32 videos. */

@@ -119,3 +119,43 @@ def test_config_streamed_corpus_equals_resident_corpus(ops):
                                            pqs, attn, K=100, precision="bf16"))
     ms, mi = ops.merge_topk(torch.stack([h[0] for h in halves]), torch.stack([h[1] for h in halves]))
     assert torch.equal(mi, i_ex) and torch.equal(ms, s_ex)
+
+
+@pytest.mark.parametrize("name", ["tvr", "charades"])
+def test_config_dense_error_within_certificate_eps(ops, name):
+    """The assumption behind engine.rank's candidate certificate, checked on EVERY (query, video) pair of a full
+    config: |approximate fused score - exact fused score| <= CERT_EPS (bf16 operands, 1e-3: the north_star
+    tolerance) resp. CERT_EPS_F16 (IEEE-half operands), after the ambiguous-key-clip pass."""
+    from dkd_b200 import engine
+    import bench
+    from dkd_b200.model import DLDKD
+    dev = torch.device("cuda")
+    shape = SHAPES[name]
+    model, frames, mask, qs = bench.synth_encoded(shape, dev, 0, DLDKD)
+    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                               T=shape["T"], heads=("two_scale",), precisions=("exact", "bf16", "fp16"))
+    pq = engine.prepare_queries([q.contiguous() for q in qs])
+    exact, _ = engine.score_two_scale_head(pc, pq, "exact")
+    for precision, eps in (("bf16", engine.CERT_EPS), ("fp16", engine.CERT_EPS_F16)):
+        approx, _ = engine.score_two_scale_head(pc, pq, precision)
+        err = float((approx - exact).abs().max())
+        assert err <= eps, f"{name}/{precision}: dense error {err:.2e} exceeds the certificate bound {eps:.1e}"
+
+
+@pytest.mark.parametrize("name,head", [("tvr", "two_scale"), ("tvr", "frame"), ("activitynet", "two_scale")])
+def test_config_fp16_rank_equals_exact_rank(ops, name, head):
+    """IEEE-half GEMM operands (precision="fp16"): same top-100 (ids and scores) as the exact path for every query."""
+    import bench
+    from dkd_b200 import engine
+    from dkd_b200.model import DLDKD
+    dev = torch.device("cuda")
+    shape = SHAPES[name]
+    model, frames, mask, qs = bench.synth_encoded(shape, dev, 0, DLDKD)
+    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                               T=shape["T"], heads=(head,), precisions=("exact", "fp16"))
+    pq = engine.prepare_queries([q.contiguous() for q in qs])
+    s_ex, i_ex = engine.rank(pc, pq, K=100, head=head, precision="exact")
+    engine.STATS["certify_fallback_queries"] = 0
+    s_h, i_h = engine.rank(pc, pq, K=100, head=head, precision="fp16", Kc=128)
+    assert torch.equal(i_h, i_ex) and torch.equal(s_h, s_ex)
+    assert engine.STATS["certify_fallback_queries"] <= pq.M // 100       # the fallback is the exception, not the path

@@ -257,6 +257,35 @@ def test_score_max_bf16(ops, M, pad, Nv, R, D, masked):
         assert (og.cpu()[~live] > 1e9).all()
 
 
+@pytest.mark.parametrize("M,pad,Nv,R,D", [(200, 256, 37, 528, 384), (50, 128, 23, 128, 384)])
+def test_score_max_f16_operands(ops, M, pad, Nv, R, D):
+    """The same GEMM on IEEE-half operands: 8 x tighter than bf16 against the fp32 oracle, accumulate-order noise
+    against an fp32 evaluation of the same half operands, proposals built directly as half rows."""
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(Nv, R, D, generator=g) + 0.5 * torch.randn(Nv, 1, D, generator=g)
+    q = torch.randn(M, D, generator=g)
+    s_ref, rows_ref, a_ref = O.get_sim_scores(q, x, None)
+    qc, xc = _cuda(q, x)
+    Mpad = ops.round_up(M, pad)
+    _, _, qh = ops.normalize_rows(qc, want_f32=False, rows_pad=Mpad, want_f16=True)
+    _, _, xh = ops.normalize_rows(xc, want_f32=False, want_f16=True)
+    om, oa = ops.score_max_bf16(qh, M, xh, Nv, R)
+    assert (om.cpu() - s_ref).abs().max() <= BF16_TOL / 8
+    rows_h = torch.einsum("md,nrd->mrn", qh[:M].float().cpu(), xh.float().cpu().view(Nv, R, D))
+    s_h, a_h = rows_h.max(dim=1)
+    assert (om.cpu() - s_h).abs().max() <= 2e-5
+    ok, nbad = _argmax_ok(oa.cpu(), rows_h, a_h, 2e-5)
+    assert ok, f"{nbad} argmax mismatches vs half-operand reference"
+    if R == 528:   # half proposal rows == half rounding of the normalised window means
+        frames, mask, lengths = synth.encoded_corpus(9, 128, D, seed=5)
+        clips = ops.downsample_clips(frames.cuda(), lengths.cuda())
+        ph, ps = ops.build_proposals_f16(clips, want_scale=True)
+        pb, ps2, _ = ops.build_proposals(clips)
+        refn = F.normalize(O.build_proposals(O.downsample_clips(frames, lengths, 32)), dim=-1)
+        assert (ph.float().cpu() - refn).abs().max() <= 2 ** -11 * refn.abs().max() + 1e-6
+        assert torch.equal(ps, ps2)
+
+
 def _branch_params(D, seed):
     g = torch.Generator().manual_seed(seed)
     kw = 0.05 * torch.randn(D, D, generator=g)

@@ -96,7 +96,7 @@ def compute_context_info(model, eval_dataset, opt):
         scoring = _opt(opt, "scoring", "frame")
         precision = _opt(opt, "precision", "exact")
         prepared = model.prepare_context(inher, explore, video_mask, heads=(scoring,),
-                                         precisions=("exact", "bf16") if precision == "bf16" else ("exact",),
+                                         precisions=("exact",) if precision == "exact" else ("exact", precision),
                                          id_base=_opt(opt, "id_base", 0))
     return dict(video_metas=metas, inher_frame_feat=inher, explore_frame_feat=explore, teacher_frame_feat=None,
                 video_mask=video_mask, prepared=prepared)
@@ -132,6 +132,8 @@ def compute_query2ctx_info(model, eval_dataset, opt, ctx_info):
     outs = [[] for _ in qs]
     for lo in range(0, qs[0].shape[0], chunk):
         pq = engine.prepare_queries([q[lo: lo + chunk] for q in qs], want_bf16=precision == "bf16")
+        if precision not in ("exact", "bf16", "fp16"):
+            raise ValueError(f"opt.precision must be 'exact', 'bf16' or 'fp16', got {precision!r}")
         if scoring == "frame":
             for o, (s, _) in zip(outs, engine.score_frame_head(pc, pq, precision)):
                 o.append(s)

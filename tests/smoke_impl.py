@@ -61,9 +61,15 @@ def run():
                 n_swapped += 1
                 assert abs(fused_ref[m, x] - fused_ref[m, y]) <= 1e-5, "exact path: ranking differs from the oracle"
     assert torch.equal(i_bf, i_ex) and torch.equal(s_bf, s_ex), "bf16+rescoring differs from the exact path"
+    # dense bf16-path scores: within the north_star tolerance of the oracle outside the tie pairs (there the
+    # oracle's key clip is a coin flip), and within it of the device's own exact path everywhere (the bound the
+    # ranking certificate relies on)
     fused_bf, _ = engine.score_two_scale_head(pc, pq, "bf16")
     d_bf = np.abs(fused_bf.cpu().numpy() - fused_ref)
-    assert np.quantile(d_bf, 0.98) <= 1e-3, "bf16 fused scores beyond 1e-3"
+    d_dev = float((fused_bf - fused_ex).abs().max())
+    assert d_bf[~tie].max() <= 1e-3, "bf16 fused scores beyond 1e-3 of the oracle"
+    assert d_dev <= engine.CERT_EPS, "bf16 fused scores beyond the certificate bound of the exact path"
     print("smoke ok: two-scale rank on cuda:0 matches the oracle "
           f"(max |d| exact {d_ex[~tie].max():.2e} outside {int(tie.sum())} fp32 key-clip ties, "
-          f"{n_swapped} near-equal swaps in the ranking, bf16 p98 {np.quantile(d_bf, 0.98):.2e} max {d_bf.max():.2e})")
+          f"{n_swapped} near-equal swaps in the ranking, bf16 vs oracle max {d_bf[~tie].max():.2e}, "
+          f"bf16 vs exact path max {d_dev:.2e})")

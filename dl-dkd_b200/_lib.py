@@ -41,7 +41,7 @@ PROTOTYPES = {
     "dkd_merge_topk": [_P, _P, _I, _I, _I, _P, _P, _P],
     "dkd_rank_of_gt": [_P, _I, _I, _L, _P, _P, _P, _P],
     "dkd_candidates_to_csr": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-    "dkd_frame_fuse_csr": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P],
+    "dkd_frame_fuse_csr": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _L, _P],
     "dkd_scatter_fuse": [_P, _P, _F, _F, _P, _P, _I, _L, _P, _P],
     "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
     "dkd_row_inv_norms": [_P, _L, _I, _F, _P, _P],

@@ -298,7 +298,8 @@ frame_fuse_csr_kernel(const float* __restrict__ q, const float* __restrict__ tab
                       const float* __restrict__ clip, const int32_t* __restrict__ key_clip,
                       const int32_t* __restrict__ vid_ptr, const int32_t* __restrict__ q_list,
                       const int32_t* __restrict__ slot, int Nv, int P, int D, float wc, float wf,
-                      float wb, int accumulate, float* __restrict__ cand_scores) {
+                      float wb, int accumulate, float* __restrict__ cand_scores, int64_t dense_ld) {
+  // dense_ld > 0: clip / key_clip are dense (M, Nv) matrices indexed by (query, video) instead of per-entry arrays
   const int n = blockIdx.x;
   const int e0 = vid_ptr[n], e1 = vid_ptr[n + 1];
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
@@ -306,15 +307,17 @@ frame_fuse_csr_kernel(const float* __restrict__ q, const float* __restrict__ tab
     const int e = base + grp;
     const bool live = e < e1;
     float acc = 0.f;
+    int64_t ce = e;
     if (live) {
-      int k = key_clip[e];
+      if (dense_ld > 0) ce = (int64_t)q_list[e] * dense_ld + n;
+      int k = key_clip[ce];
       k = k < 0 ? 0 : (k >= P ? P - 1 : k);
       acc = RowLoader<float>::dot(q + (int64_t)q_list[e] * D, table + ((int64_t)n * P + k) * D, D, sub);
     }
 #pragma unroll
     for (int s = 4; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (live && sub == 0) {
-      const float v = fuse_branch(clip[e], acc, wc, wf, wb);
+      const float v = fuse_branch(clip[ce], acc, wc, wf, wb);
       const int sl = slot[e];
       cand_scores[sl] = accumulate ? __fadd_rn(cand_scores[sl], v) : v;
     }
@@ -417,15 +420,16 @@ extern "C" int dkd_frame_fuse_csr(const float* q, const float* table, const floa
                                   const int32_t* key_clip, const int32_t* vid_ptr, const int32_t* q_list,
                                   const int32_t* slot, int32_t Nv, int32_t P, int32_t D, float w_clip,
                                   float w_frame, float w_branch, int32_t accumulate, float* cand_scores,
-                                  void* stream) {
+                                  int64_t dense_ld, void* stream) {
   if (!q || !table || !clip_scores || !key_clip || !vid_ptr || !q_list || !slot || !cand_scores || Nv < 0)
     return DKD_ERR_ARG;
+  if (dense_ld != 0 && dense_ld < Nv) return DKD_ERR_ARG;
   if (D <= 0 || D % 32 != 0 || P <= 0) return DKD_ERR_SHAPE;
   if (Nv == 0) return DKD_OK;
   dim3 grid(Nv, 4);
   frame_fuse_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, table, clip_scores, key_clip, vid_ptr,
                                                                 q_list, slot, Nv, P, D, w_clip, w_frame,
-                                                                w_branch, accumulate, cand_scores);
+                                                                w_branch, accumulate, cand_scores, dense_ld);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -120,7 +120,7 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
             key = F.linear(fr, kw, kb).contiguous()
             val = F.linear(fr, vw, vb).contiguous()
             bd.table_f, bd.table_h = ops.frame_attn_table(key, val, bd.clips, lengths, want_f32=True,
-                                                          want_f16="bf16" in precisions or "fp16" in precisions)
+                                                          want_f16=any(x in precisions for x in ("bf16", "fp16", "shortcut")))
             del key, val
         pc.branches.append(bd)
     return pc
@@ -202,6 +202,11 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
         if precision == "exact":
             s_clip, k_clip = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale)
             q, tab = qn, bd.table_f
+        elif precision == "shortcut":
+            # exact clip scale through the linearity shortcut (32 per-clip dots on tcgen05 kind::tf32 x 3 + window
+            # scan): exact key clips for EVERY pair, so no ambiguity pass; only the frame-scale gather is approximate
+            s_clip, k_clip = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale)
+            q, tab = qh, bd.table_h
         else:
             if precision == "fp16":
                 qb, prop = qh, bd.prop_h
@@ -245,11 +250,14 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
         dev = pc.mask_u8.device
         return (torch.full((pq.M, K), float("-inf"), dtype=torch.float32, device=dev),
                 torch.full((pq.M, K), -1, dtype=torch.int32, device=dev))
+    per = None
     if head == "frame":
+        if precision == "shortcut":
+            raise ValueError("precision='shortcut' is a two-scale variant (the frame head has no clip windows)")
         sc = score_frame_head(pc, pq, precision)
         fused = sc[0][0] if nb == 1 else ops.fuse_scores(sc[0][0], sc[1][0], wbs[0], wbs[1])
     else:
-        fused, _ = score_two_scale_head(pc, pq, precision, w_clip, w_frame, tau=tau)
+        fused, per = score_two_scale_head(pc, pq, precision, w_clip, w_frame, tau=tau)
     if precision == "exact" or not rescore:
         return ops.topk(fused, K, pc.id_base)
     Kc = max(Kc, K)
@@ -264,12 +272,15 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             ops.scatter_fuse(ex[0], None, 1.0, 0.0, csr, cand_scores)
     else:
         for bi, (bd, qn) in enumerate(zip(pc.branches, pq.qn)):
-            cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2])
+            if precision == "shortcut":     # the dense clip scores / key clips are already exact
+                cs, ck = per[bi]["clip"], per[bi]["key_clip"]
+            else:
+                cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2])
             wb = wbs[bi] if nb == 2 else 1.0
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
     out_s, out_i = ops.sort_candidates(cand_scores, cand, K)
     if certify and Kc < pc.Nv:
-        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + (CERT_EPS_F16 if precision == "fp16" else CERT_EPS)
+        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + (CERT_EPS if precision == "bf16" else CERT_EPS_F16)
         n_unsure = int(unsure.sum())
         STATS["certify_checked_queries"] += pq.M
         STATS["certify_fallback_queries"] += n_unsure

@@ -357,12 +357,16 @@ def candidates_to_csr(cand_ids, Nv, id_base=0):
 
 
 def frame_fuse_csr(q, table, clip_scores, key_clip, csr, w_clip, w_frame, w_branch, cand_scores, accumulate):
+    """clip_scores / key_clip: per-entry (E,) arrays, or dense (M, Nv) matrices (read at (query, video) of each entry)."""
     _chk(q, torch.float32, "q")
     _chk(table, torch.float32, "table")
+    _chk(clip_scores, torch.float32, "clip_scores")
+    _chk(key_clip, torch.int32, "key_clip")
     vid_ptr, q_list, slot = csr
     Nv, P, D = table.shape
+    dense_ld = clip_scores.shape[1] if clip_scores.dim() == 2 else 0
     _lib.call("dkd_frame_fuse_csr", _p(q), _p(table), _p(clip_scores), _p(key_clip), _p(vid_ptr), _p(q_list),
-              _p(slot), Nv, P, D, w_clip, w_frame, w_branch, int(accumulate), _p(cand_scores), _stream())
+              _p(slot), Nv, P, D, w_clip, w_frame, w_branch, int(accumulate), _p(cand_scores), dense_ld, _stream())
     return cand_scores
 
 

@@ -219,12 +219,14 @@ int dkd_rank_of_gt(const float* scores, int32_t M, int32_t Nv, int64_t ld, const
 int dkd_candidates_to_csr(const int32_t* cand_ids, int32_t M, int32_t K, int32_t Nv,
                           int32_t id_base, int32_t* counts, int32_t* vid_ptr, int32_t* q_list,
                           int32_t* slot, void* stream);
-/* Per-CSR-entry frame score + fusion (exact rescoring of candidates), then scatter to (M, K). */
+/* Per-CSR-entry frame score + fusion (exact rescoring of candidates), then scatter to (M, K).
+ * clip_scores / key_clip: per-entry arrays (dense_ld = 0), or dense (M, ld) matrices read at (q_list[e], video)
+ * (dense_ld = ld >= Nv) when the exact clip scores of every pair already exist. */
 int dkd_frame_fuse_csr(const float* q, const float* table, const float* clip_scores,
                        const int32_t* key_clip, const int32_t* vid_ptr, const int32_t* q_list,
                        const int32_t* slot, int32_t Nv, int32_t P, int32_t D, float w_clip,
                        float w_frame, float w_branch, int32_t accumulate, float* cand_scores,
-                       void* stream);
+                       int64_t dense_ld, void* stream);
 /* Per-CSR-entry fusion + scatter (reference frame path rescoring): out[slot[e]] =
  * fl(wa*a[e]) + fl(wb*b[e]) for e < vid_ptr[Nv] (b == NULL: plain scatter of a). */
 int dkd_scatter_fuse(const float* a, const float* b, float wa, float wb, const int32_t* slot,

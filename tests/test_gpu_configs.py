@@ -159,3 +159,33 @@ def test_config_fp16_rank_equals_exact_rank(ops, name, head):
     s_h, i_h = engine.rank(pc, pq, K=100, head=head, precision="fp16", Kc=128)
     assert torch.equal(i_h, i_ex) and torch.equal(s_h, s_ex)
     assert engine.STATS["certify_fallback_queries"] <= pq.M // 100       # the fallback is the exception, not the path
+
+
+@pytest.mark.parametrize("name", ["tvr", "charades"])
+def test_config_shortcut_rank_equals_exact_rank(ops, name):
+    """precision="shortcut" (exact clip scores for every pair via the linearity shortcut, approximate fp16 frame
+    gather, exact frame rescoring of the candidates): same top-100 as the all-exact path for every query; its dense
+    scores differ from the exact ones only by the fp16 frame term."""
+    import bench
+    from dkd_b200 import engine
+    from dkd_b200.model import DLDKD
+    dev = torch.device("cuda")
+    shape = SHAPES[name]
+    model, frames, mask, qs = bench.synth_encoded(shape, dev, 0, DLDKD)
+    if name == "charades":
+        g = torch.Generator(device=dev).manual_seed(77)
+        lengths = torch.randint(64, shape["L"] + 1, (shape["Nv"],), device=dev, generator=g)
+        mask = (torch.arange(shape["L"], device=dev)[None] < lengths[:, None]).float()
+        frames = [f * mask[:, :, None] for f in frames]
+    pc = engine.prepare_corpus(frames, mask, [tuple(t.detach() for t in p) for p in model.attention_params()],
+                               T=shape["T"], heads=("two_scale",), precisions=("exact", "shortcut"))
+    assert pc.branches[0].prop_b is None and pc.branches[0].prop_h is None      # no GEMM operand at all
+    pq = engine.prepare_queries([q.contiguous() for q in qs])
+    s_ex, i_ex = engine.rank(pc, pq, K=100, head="two_scale", precision="exact")
+    engine.STATS["certify_fallback_queries"] = 0
+    s_sc, i_sc = engine.rank(pc, pq, K=100, head="two_scale", precision="shortcut", Kc=128)
+    assert torch.equal(i_sc, i_ex) and torch.equal(s_sc, s_ex)
+    assert engine.STATS["certify_fallback_queries"] <= pq.M // 100
+    exact, _ = engine.score_two_scale_head(pc, pq, "exact")
+    approx, per = engine.score_two_scale_head(pc, pq, "shortcut")
+    assert float((approx - exact).abs().max()) <= engine.CERT_EPS_F16

@@ -217,7 +217,7 @@ exact_umma_kernel(const ExactParams p) {
         const uint32_t it = it_base + (uint32_t)j;
         const uint32_t stage = it % (uint32_t)kXStages;
         const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
-        mbar_wait(&ctl->a_empty[stage], phase ^ 1u);
+        mbar_wait_backoff(&ctl->a_empty[stage], phase ^ 1u, 200);
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -271,7 +271,7 @@ exact_umma_kernel(const ExactParams p) {
         if (count <= 0) continue;
         if (kMode == 0) {
           const uint32_t bb = vi % b_bufs;
-          mbar_wait(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u);
+          mbar_wait_backoff(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u, 200);
           ++vi;
           mbar_expect_tx(&ctl->b_full[bb], b_buf_bytes);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * b_buf_bytes;
@@ -284,7 +284,7 @@ exact_umma_kernel(const ExactParams p) {
           for (int t0 = 0; t0 < count; t0 += kXRows) {
             for (int kb = 0; kb < num_kb; ++kb, ++itb) {
               const uint32_t bs = itb % (uint32_t)kXBStages;
-              mbar_wait(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u);
+              mbar_wait_backoff(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u, 200);
               mbar_expect_tx(&ctl->b_full[bs], b_buf_bytes);
               bulk_load(sB + (size_t)bs * b_buf_bytes, src + (size_t)kb * b_buf_bytes, b_buf_bytes, &ctl->b_full[bs]);
             }
@@ -307,12 +307,12 @@ exact_umma_kernel(const ExactParams p) {
       uint32_t bb = 0;
       if (kMode == 0) {
         bb = vi % b_bufs;
-        mbar_wait(&ctl->b_full[bb], (vi / b_bufs) & 1u);
+        mbar_wait_backoff(&ctl->b_full[bb], (vi / b_bufs) & 1u, 40);
         ++vi;
       }
       for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
         const uint32_t buf = tc & 1u;
-        mbar_wait(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u);
+        mbar_wait_backoff(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u, 40);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)kDW;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -321,10 +321,10 @@ exact_umma_kernel(const ExactParams p) {
           uint32_t bs = 0;
           if (kMode == 1) {
             bs = itb % (uint32_t)kXBStages;
-            mbar_wait(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u);
+            mbar_wait_backoff(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u, 40);
             ++itb;
           }
-          mbar_wait(&ctl->a_full[stage], phase);
+          mbar_wait_backoff(&ctl->a_full[stage], phase, 40);
           tc_fence_after();
           if (elected) {
             const uint32_t a_hi = tmem_base + kXACol0 + stage * 64u;

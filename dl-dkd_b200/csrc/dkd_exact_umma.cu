@@ -23,6 +23,8 @@
 //               (512 columns: 2 x 32 accumulator + 7 x 64 A ring)
 //   warp 13     B loader: one cp.async.bulk per video of its pre-packed clip planes (dkd_pack_clips_tf32: the
 //               shared-memory image of the B operand — tf32 hi / lo planes, K-major SWIZZLE_128B)
+#include <cstdlib>
+
 #include "dkd_umma.cuh"
 
 namespace dkd {
@@ -53,6 +55,7 @@ struct ExactParams {
   const uint8_t* mask;         // rows mode: (Nv, R) or null
   float* out_max; int32_t* out_arg; int64_t ld_out;
   const int32_t* vid_ptr; const int32_t* vid_cnt; const int32_t* q_list; const int32_t* out_slot;
+  unsigned wait_ns;            // sleep between mbarrier polls of the non-critical warps (0: spin)
 };
 
 struct __align__(8) ExactCtl {
@@ -217,7 +220,7 @@ exact_umma_kernel(const ExactParams p) {
         const uint32_t it = it_base + (uint32_t)j;
         const uint32_t stage = it % (uint32_t)kXStages;
         const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
-        mbar_wait_backoff(&ctl->a_empty[stage], phase ^ 1u, 200);
+        mbar_wait_backoff(&ctl->a_empty[stage], phase ^ 1u, 5 * p.wait_ns);
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -271,7 +274,7 @@ exact_umma_kernel(const ExactParams p) {
         if (count <= 0) continue;
         if (kMode == 0) {
           const uint32_t bb = vi % b_bufs;
-          mbar_wait_backoff(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u, 200);
+          mbar_wait_backoff(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u, 5 * p.wait_ns);
           ++vi;
           mbar_expect_tx(&ctl->b_full[bb], b_buf_bytes);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * b_buf_bytes;
@@ -284,7 +287,7 @@ exact_umma_kernel(const ExactParams p) {
           for (int t0 = 0; t0 < count; t0 += kXRows) {
             for (int kb = 0; kb < num_kb; ++kb, ++itb) {
               const uint32_t bs = itb % (uint32_t)kXBStages;
-              mbar_wait_backoff(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u, 200);
+              mbar_wait_backoff(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u, 5 * p.wait_ns);
               mbar_expect_tx(&ctl->b_full[bs], b_buf_bytes);
               bulk_load(sB + (size_t)bs * b_buf_bytes, src + (size_t)kb * b_buf_bytes, b_buf_bytes, &ctl->b_full[bs]);
             }
@@ -307,12 +310,12 @@ exact_umma_kernel(const ExactParams p) {
       uint32_t bb = 0;
       if (kMode == 0) {
         bb = vi % b_bufs;
-        mbar_wait_backoff(&ctl->b_full[bb], (vi / b_bufs) & 1u, 40);
+        mbar_wait_backoff(&ctl->b_full[bb], (vi / b_bufs) & 1u, p.wait_ns);
         ++vi;
       }
       for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
         const uint32_t buf = tc & 1u;
-        mbar_wait_backoff(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u, 40);
+        mbar_wait_backoff(&ctl->tmem_empty[buf], ((tc >> 1) & 1u) ^ 1u, p.wait_ns);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)kDW;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -321,10 +324,10 @@ exact_umma_kernel(const ExactParams p) {
           uint32_t bs = 0;
           if (kMode == 1) {
             bs = itb % (uint32_t)kXBStages;
-            mbar_wait_backoff(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u, 40);
+            mbar_wait_backoff(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u, p.wait_ns);
             ++itb;
           }
-          mbar_wait_backoff(&ctl->a_full[stage], phase, 40);
+          mbar_wait_backoff(&ctl->a_full[stage], phase, p.wait_ns);
           tc_fence_after();
           if (elected) {
             const uint32_t a_hi = tmem_base + kXACol0 + stage * 64u;
@@ -538,6 +541,7 @@ extern "C" int dkd_pack_rows_tf32(const float* xn, int32_t Nv, int32_t R, int32_
 
 // shared launcher: mode 0 (clip windows) / mode 1 (rows max)
 static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStream_t st) {
+  { const char* e = getenv("DKD_EXACT_WAIT_NS"); p.wait_ns = e ? (unsigned)atoi(e) : 0u; }   // A/B on one box: no gain from sleeping
   int dev = 0, sms = 0, max_smem = 0;
   DKD_CUDA_TRY(cudaGetDevice(&dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) scan_kernel(const float* __res
   const long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
+    asm volatile("" ::: "memory");   // like the kernel's mbarrier wait: the scale loads may not be hoisted out of the tile loop
     float d[32], run[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) d[i] = sd[i][threadIdx.x] + (float)it * 1e-3f;
@@ -104,6 +105,78 @@ __device__ __forceinline__ void scan_range(const float (*sd)[8 * 32 + 1], const 
   obv = bv[0]; obi = bi[0];
 }
 
+// Start-major scan: one chain per window start s (running sum over w, local first maximum by strict >), kIl starts
+// interleaved for ILP, scale read from a TRANSPOSED table sc_t[s][w - 1] in 4-wide loads consumed immediately; chains
+// merge into the global best with the full (value desc, proposal asc) rule.  Small register footprint.
+template <int kIl>
+__global__ void __launch_bounds__(128, 1) scan_smajor_kernel(const float* __restrict__ dots, const float* __restrict__ scale,
+                                                            int iters, float* __restrict__ out_v, int* __restrict__ out_i,
+                                                            long long* cycles) {
+  __shared__ __align__(16) float sct[32 * 32];
+  __shared__ float sd[32][4 * 32 + 1];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sct[(i & 31) * 32 + (i >> 5)] = scale[i];   // [s][w - 1]
+  for (int i = 0; i < 32; ++i) sd[i][threadIdx.x] = dots[(blockIdx.x * blockDim.x + threadIdx.x) * 32 + i];
+  __syncthreads();
+  float accv = 0.f; int acci = 0;
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    asm volatile("" ::: "memory");
+    float d[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = sd[i][threadIdx.x] + (float)it * 1e-3f;
+    float gv = -INFINITY; int gi = 0x7fffffff;
+#pragma unroll
+    for (int s0 = 0; s0 < 32; s0 += kIl) {
+      float run[kIl], bv[kIl]; int bi[kIl];
+#pragma unroll
+      for (int c = 0; c < kIl; ++c) { bv[c] = -INFINITY; bi[c] = 0x7fffffff; }
+#pragma unroll
+      for (int w0 = 0; w0 < 32 - s0; w0 += 4) {          // window lengths w0 + 1 .. w0 + 4
+        float4 sc4[kIl];
+#pragma unroll
+        for (int c = 0; c < kIl; ++c)
+          if (s0 + c + w0 < 32) sc4[c] = *reinterpret_cast<const float4*>(&sct[(s0 + c) * 32 + w0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int w = w0 + j + 1;
+#pragma unroll
+          for (int c = 0; c < kIl; ++c) {
+            const int s = s0 + c;
+            if (s + w <= 32) {
+              run[c] = (w == 1) ? d[s] : __fadd_rn(run[c], d[s + w - 1]);
+              const int pi = (w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s;
+              const float scl = j == 0 ? sc4[c].x : (j == 1 ? sc4[c].y : (j == 2 ? sc4[c].z : sc4[c].w));
+              const float v = __fmul_rn(run[c], scl);
+              if (v > bv[c]) { bv[c] = v; bi[c] = pi; }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kIl; ++c)
+        if (better(bv[c], bi[c], gv, gi)) { gv = bv[c]; gi = bi[c]; }
+    }
+    accv += gv; acci += gi;
+  }
+  const long long t1 = clock64();
+  out_v[blockIdx.x * blockDim.x + threadIdx.x] = accv;
+  out_i[blockIdx.x * blockDim.x + threadIdx.x] = acci;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int kIl>
+void run_smajor(const float* dots, const float* scale, float* ov, int* oi, long long* cyc, int iters) {
+  for (int rep = 0; rep < 2; ++rep) {
+    scan_smajor_kernel<kIl><<<148, 128>>>(dots, scale, iters, ov, oi, cyc);
+    cudaDeviceSynchronize();
+  }
+  long long h[148];
+  cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+  printf("start-major scan, %d starts interleaved, 1 warp per scheduler:  %6.0f cycles per scheduler per 128-row tile\n", kIl, avg / iters);
+}
+
 template <int kSplit>
 __global__ void __launch_bounds__(256, 1) scan_split_kernel(const float* __restrict__ dots, const float* __restrict__ scale,
                                                            int iters, float* __restrict__ out_v, int* __restrict__ out_i,
@@ -120,6 +193,7 @@ __global__ void __launch_bounds__(256, 1) scan_split_kernel(const float* __restr
   const long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
+    asm volatile("" ::: "memory");
     float bv; int bi;
     if (part == 0) scan_range<0, kSplit>(sd, sc, it, bv, bi);
     else scan_range<kSplit, 32>(sd, sc, it, bv, bi);
@@ -177,6 +251,9 @@ int main() {
   run<2, 4>("2 values only (fmaxf)", dots, scale, ov, oi, cyc, 200);
   run<3, 4>("3 scale row prefetched one w ahead", dots, scale, ov, oi, cyc, 200);
   run<4, 4>("4 16 running maxima", dots, scale, ov, oi, cyc, 200);
+  run_smajor<4>(dots, scale, ov, oi, cyc, 200);
+  run_smajor<8>(dots, scale, ov, oi, cyc, 200);
+  run_smajor<16>(dots, scale, ov, oi, cyc, 200);
   run_split<10>(dots, scale, ov, oi, cyc, 200);
   run_split<8>(dots, scale, ov, oi, cyc, 200);
   run_split<12>(dots, scale, ov, oi, cyc, 200);

@@ -56,7 +56,10 @@ struct ExactParams {
   float* out_max; int32_t* out_arg; int64_t ld_out;
   const int32_t* vid_ptr; const int32_t* vid_cnt; const int32_t* q_list; const int32_t* out_slot;
   unsigned wait_ns;            // sleep between mbarrier polls of the non-critical warps (0: spin)
+  // mode 2 (dense clip windows, kXGroup videos per tile): Nv = number of WORK ITEMS = video groups x tile chunks
+  int Nv_real, tile_chunks, tiles_per_chunk;
 };
+constexpr int kXGroup = 4;                   // mode 2: videos sharing one staged A tile (UMMA N = 4 x 32 clips)
 
 struct __align__(8) ExactCtl {
   uint64_t a_full[kXMaxAStages], a_empty[kXMaxAStages];
@@ -120,17 +123,37 @@ __device__ __forceinline__ void video_range(const ExactParams& p, int n, int& e0
   else { e0 = 0; count = p.M; }
 }
 
+// mode 2 work item -> (video group, first query row, number of query rows)
+__device__ __forceinline__ void item_range(const ExactParams& p, int item, int& group, int& row0, int& count) {
+  group = item / p.tile_chunks;
+  const int chunk = item - group * p.tile_chunks;
+  row0 = chunk * p.tiles_per_chunk * kXRows;
+  const int rows = p.tiles_per_chunk * kXRows;
+  count = p.M - row0 < rows ? p.M - row0 : rows;
+}
+
 // kMode 0: clip windows (B = the video's 32 clips, resident; scan = T(T+1)/2 window cosines).
 // kMode 1: rows max (B = the video's R <= 128 rows, streamed per K block through a ring; scan = masked max).
+// kMode 2: clip windows, DENSE only.  Measurements (tools/micro/scan_micro.cu): one window scan is a
+//          latency-bound instruction stream (7.4 k cycles per 32 rows in isolation, ~9.9 k next to the stagers) and it
+//          paces the whole kernel; two independent scans per scheduler overlap perfectly.  So mode 2 runs TWO scan
+//          groups (warps 0-3 take the even tiles = accumulator buffer 0, warps 8-11 the odd tiles = buffer 1) and
+//          pays for the second group with stager warps: kXGroup = 4 videos share every staged A tile (their clip planes
+//          form one N = 128 B operand, streamed per K block like mode 1), which cuts the staging work per pair 4 x, so
+//          one stager warp per TMEM lane quarter (warps 4-7) is enough.  Same 14 warps, same 128 registers per thread.
+//          Modes 0 / 1 keep one scan group and two stager sets (list forms: every video has its own query list).
 template <int kMode, bool kT32, int kXRing>
 __global__ void __launch_bounds__(kXThreads, 1)
 exact_umma_kernel(const ExactParams p) {
   constexpr int kDW = kMode == 0 ? 32 : 128;                    // accumulator columns per TMEM buffer
+  constexpr int kScaleBufs = kMode == 2 ? kXGroup : 2;
+  constexpr int kStageSets = kMode == 2 ? 1 : 2;                // stager warps per TMEM lane quarter
   constexpr uint32_t kXACol0 = 2 * kDW;                         // first A-ring column
   constexpr int kXStages = (kXTmemCols - 2 * kDW) / 64;         // A ring stages: 7 / 4
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
-  __shared__ __align__(16) float s_scale[2][32 * 32];   // prop_scale of the current video as [w - 1][s] (scan warps,
-                                                        // double buffered): 16-byte loads at compile-time offsets
+  __shared__ __align__(16) float s_scale[kScaleBufs][32 * 32];   // prop_scale of the current video(s) as [w - 1][s]
+                                                        // (scan warps; mode 0: double buffered): 16-byte loads at
+                                                        // compile-time offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_x) + 1023) & ~(uintptr_t)1023);
   const int num_kb = p.D / kXKB;
   // mode 0: [buf][kb][plane] x 4 KB, one buffer per video; mode 1: [stage][plane] x Npad x 128 B, one stage per K block
@@ -159,13 +182,13 @@ exact_umma_kernel(const ExactParams p) {
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp >= kXScanWarps && warp < kXMmaWarp) {
+  if (warp >= kXScanWarps && warp < kXScanWarps + 4 * kStageSets) {
     // ===================== stagers =====================
     // Query rows are gathered as fp32 (coalesced 128-byte row segments) by cp.async into a private per-warp
     // ring (kXRing - 1 K blocks in flight per warp: the gather is latency bound, the bytes in flight set its
     // bandwidth), read back as tcgen05.st.16x256b fragments, split into tf32 hi / lo and stored to the TMEM A
     // ring, whose 7 stages decouple the stagers from the MMA.
-    const int quarter = warp & 3, par = (warp - kXScanWarps) >> 2;   // this warp stages items j = par (mod 2)
+    const int quarter = warp & 3, par = (warp - kXScanWarps) >> 2;   // this warp stages items j = par (mod kStageSets)
     const int g = lane >> 2, t = lane & 3;
     const int cl_row = lane >> 3, cl_chunk = lane & 7;          // cp.async: 4 rows x 8 chunks per instruction
     const uint32_t a_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + kXACol0;
@@ -174,8 +197,9 @@ exact_umma_kernel(const ExactParams p) {
     const uint8_t* ring_ptr = sS + (size_t)sw * kXRing * kXSlotBytes;
     uint32_t it_base = 0;                                       // A ring counter of item 0 of the current video
     for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
-      int e0, count;
-      video_range(p, n, e0, count);
+      int e0, count, row_base = 0;
+      if (kMode == 2) { int g_; item_range(p, n, g_, row_base, count); e0 = 0; }
+      else video_range(p, n, e0, count);
       if (count <= 0) continue;
       const int nitems = ((count + kXRows - 1) / kXRows) * num_kb;
       // item j = (tile j / num_kb, K block j % num_kb) of this video
@@ -186,7 +210,7 @@ exact_umma_kernel(const ExactParams p) {
       while (iss_kb >= num_kb) { iss_kb -= num_kb; ++iss_tile; }
       auto issue = [&](int slot) {
         const int tile = iss_tile, kb = iss_kb;
-        iss_kb += 2;
+        iss_kb += kStageSets;
         while (iss_kb >= num_kb) { iss_kb -= num_kb; ++iss_tile; }
         if (tile != t_cached) {
           t_cached = tile;
@@ -195,7 +219,7 @@ exact_umma_kernel(const ExactParams p) {
           for (int i = 0; i < 8; ++i) {
             const int r = tile * kXRows + quarter * 32 + 4 * i + cl_row;
             const bool live = r < count;
-            const int64_t qrow = live ? (p.q_list ? (int64_t)p.q_list[e0 + r] : (int64_t)r) : 0;
+            const int64_t qrow = live ? (p.q_list ? (int64_t)p.q_list[e0 + r] : (int64_t)(row_base + r)) : 0;
             src_cached[i] = p.q + qrow * p.D + 4 * cl_chunk;
             live_mask |= (live ? 1u : 0u) << i;
           }
@@ -247,7 +271,7 @@ exact_umma_kernel(const ExactParams p) {
       };
       // this warp's items: j = 2m + par.  Prologue: the first kXRing - 1 of them (one commit group per item,
       // empty groups keep the count uniform)
-      const int nmine = (nitems - par + 1) / 2;
+      const int nmine = (nitems - par + kStageSets - 1) / kStageSets;
 #pragma unroll
       for (int m = 0; m < kXRing - 1; ++m) {
         if (m < nmine) issue(m);
@@ -258,7 +282,7 @@ exact_umma_kernel(const ExactParams p) {
         cp_async_commit();
         cp_async_wait<kXRing - 1>();                            // item m has landed
         __syncwarp();
-        store(2 * m + par, m % kXRing);
+        store(kStageSets * m + par, m % kXRing);
         __syncwarp();                                           // every lane is done with the slot
       }
       cp_async_wait<0>();
@@ -270,6 +294,29 @@ exact_umma_kernel(const ExactParams p) {
       uint32_t vi = 0, itb = 0;
       for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
         int e0, count;
+        if (kMode == 2) {
+          // the 4 videos' pre-packed clip planes (4 KB per video, plane and K block) land side by side: rows 32 v ..
+          // 32 v + 31 of the N = 128 operand; a missing video (tail group) re-reads the last one, its columns are ignored
+          int g_, row0_;
+          item_range(p, n, g_, row0_, count);
+          if (count <= 0) continue;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(p.planes);
+          for (int t0 = 0; t0 < count; t0 += kXRows) {
+            for (int kb = 0; kb < num_kb; ++kb, ++itb) {
+              const uint32_t bs = itb % (uint32_t)kXBStages;
+              mbar_wait_backoff(&ctl->b_empty[bs], ((itb / (uint32_t)kXBStages) & 1u) ^ 1u, 5 * p.wait_ns);
+              mbar_expect_tx(&ctl->b_full[bs], b_buf_bytes);
+              for (int v = 0; v < kXGroup; ++v) {
+                const int vid = min(g_ * kXGroup + v, p.Nv_real - 1);
+                const uint8_t* src = base + ((size_t)vid * num_kb + kb) * 2 * kXBPlane;
+                bulk_load(sB + (size_t)bs * b_buf_bytes + (size_t)v * kXBPlane, src, kXBPlane, &ctl->b_full[bs]);
+                bulk_load(sB + (size_t)bs * b_buf_bytes + (size_t)(kXGroup + v) * kXBPlane, src + kXBPlane, kXBPlane,
+                          &ctl->b_full[bs]);
+              }
+            }
+          }
+          continue;
+        }
         video_range(p, n, e0, count);
         if (count <= 0) continue;
         if (kMode == 0) {
@@ -305,7 +352,8 @@ exact_umma_kernel(const ExactParams p) {
     uint32_t it = 0, vi = 0, tc = 0, itb = 0;
     for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
       int e0, count;
-      video_range(p, n, e0, count);
+      if (kMode == 2) { int g_, r_; item_range(p, n, g_, r_, count); e0 = 0; }
+      else video_range(p, n, e0, count);
       if (count <= 0) continue;
       uint32_t bb = 0;
       if (kMode == 0) {
@@ -322,7 +370,7 @@ exact_umma_kernel(const ExactParams p) {
           const uint32_t stage = it % (uint32_t)kXStages;
           const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
           uint32_t bs = 0;
-          if (kMode == 1) {
+          if (kMode != 0) {
             bs = itb % (uint32_t)kXBStages;
             mbar_wait_backoff(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u, p.wait_ns);
             ++itb;
@@ -342,7 +390,7 @@ exact_umma_kernel(const ExactParams p) {
               umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
             }
             umma_commit(&ctl->a_empty[stage]);
-            if (kMode == 1) umma_commit(&ctl->b_empty[bs]);
+            if (kMode != 0) umma_commit(&ctl->b_empty[bs]);
           }
           __syncwarp();
         }
@@ -352,6 +400,85 @@ exact_umma_kernel(const ExactParams p) {
       if (kMode == 0) {
         if (elected) umma_commit(&ctl->b_empty[bb]);
         __syncwarp();
+      }
+    }
+  } else if constexpr (kMode == 2) {
+    // ===================== scan: clip windows of kXGroup videos per tile, two groups alternating tiles ================
+    // Same per-row arithmetic as mode 0 (sequential window sums, x scale, strict > in proposal order); the 4 videos'
+    // dots sit in accumulator columns 32 v .. 32 v + 31.
+    const int T = p.T, P = T * (T + 1) / 2;
+    const int quarter = warp & 3;
+    const uint32_t part = warp >= 2 * kXScanWarps ? 1u : 0u;        // warps 0-3: even tiles, warps 8-11: odd tiles
+    const int stid = threadIdx.x;
+    uint32_t tc = 0;
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int group, row0, count;
+      item_range(p, n, group, row0, count);
+      if (count <= 0) continue;
+      asm volatile("bar.sync 1, %0;" ::"n"(2 * kXScanWarps * 32) : "memory");   // previous item's tables are dead
+      if (part == 0) {
+        for (int v = 0; v < kXGroup; ++v) {
+          const int vid = min(group * kXGroup + v, p.Nv_real - 1);
+          const float* gsc = p.scale + (int64_t)vid * P;
+          const int s_ = stid & 31;
+          int base = 0;
+          for (int w = 1; w <= T; ++w) {
+            if ((w & 3) == (stid >> 5) && s_ + w <= T) s_scale[v][(w - 1) * 32 + s_] = __ldg(gsc + base + s_);
+            base += T - w + 1;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(2 * kXScanWarps * 32) : "memory");
+      for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
+        const uint32_t buf = tc & 1u;
+        if (buf != part) continue;
+        mbar_wait(&ctl->tmem_full[buf], (tc >> 1) & 1u);
+        tc_fence_after();
+        const int r = row0 + t0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int v = 0; v < kXGroup; ++v) {
+          uint32_t raw[32];
+          tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)kDW + (uint32_t)(32 * v), raw);
+          tmem_ld_wait();
+          if (v == kXGroup - 1) {                 // the accumulator buffer is free once its last slice is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+          }
+          const float* sc = s_scale[v];
+          float d[32], run[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
+          float bv[8];
+          int bi[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
+#pragma unroll
+          for (int w = 1; w <= 32; ++w) {
+            float scw[32];
+#pragma unroll
+            for (int s4 = 0; s4 + w <= 32; s4 += 4)
+              *reinterpret_cast<float4*>(&scw[s4]) = *reinterpret_cast<const float4*>(&sc[(w - 1) * 32 + s4]);
+#pragma unroll
+            for (int s = 0; s + w <= 32; ++s) {
+              run[s] = (w == 1) ? d[s] : __fadd_rn(run[s], d[s + w - 1]);
+              if (kT32 || s + w <= T) {
+                const int pi = kT32 ? ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s) : ((w - 1) * T - ((w - 1) * (w - 2)) / 2 + s);
+                const float val = __fmul_rn(run[s], scw[s]);
+                if (val > bv[s & 7]) { bv[s & 7] = val; bi[s & 7] = pi; }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 1; k < 8; ++k)
+            if (better(bv[k], bi[k], bv[0], bi[0])) { bv[0] = bv[k]; bi[0] = bi[k]; }
+          const int vid = group * kXGroup + v;
+          if (r < p.M && t0 + quarter * 32 + lane < count && vid < p.Nv_real) {
+            const int64_t o = (int64_t)r * p.ld_out + vid;
+            p.out_max[o] = bv[0];
+            if (p.out_arg) p.out_arg[o] = bi[0];
+          }
+        }
       }
     }
   } else if constexpr (kMode == 0) {
@@ -548,7 +675,8 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_kb = D / kXKB;
   const int ring = D > 448 ? 2 : 3;
-  const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 8192 /* static shared */ + (size_t)kXStageWarps * ring * kXSlotBytes;
+  const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 16384 /* static shared, largest mode */ +
+                       (size_t)kXStageWarps * ring * kXSlotBytes;
   size_t b_total;
   if (mode == 0) {
     const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
@@ -560,7 +688,7 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
     b_total = (size_t)kXBStages * 2 * p.Npad * 128;
     if ((size_t)max_smem < fixed + b_total) return DKD_ERR_SHAPE;
   }
-  const size_t smem = fixed - 8192 + b_total;
+  const size_t smem = fixed - 16384 + b_total;
   const int grid = p.Nv < sms ? p.Nv : sms;
   auto launch = [&](auto kern) -> int {
     DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -571,6 +699,9 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
   if (mode == 0) {
     if (ring == 3) rc = (T == 32) ? launch(exact_umma_kernel<0, true, 3>) : launch(exact_umma_kernel<0, false, 3>);
     else rc = (T == 32) ? launch(exact_umma_kernel<0, true, 2>) : launch(exact_umma_kernel<0, false, 2>);
+  } else if (mode == 2) {
+    if (ring == 3) rc = (T == 32) ? launch(exact_umma_kernel<2, true, 3>) : launch(exact_umma_kernel<2, false, 3>);
+    else rc = (T == 32) ? launch(exact_umma_kernel<2, true, 2>) : launch(exact_umma_kernel<2, false, 2>);
   } else {
     rc = (ring == 3) ? launch(exact_umma_kernel<1, true, 3>) : launch(exact_umma_kernel<1, true, 2>);
   }
@@ -613,5 +744,21 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
   p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
   p.vid_ptr = vid_ptr; p.vid_cnt = vid_cnt; p.q_list = q_list; p.out_slot = out_slot;
+  const char* force0 = getenv("DKD_EXACT_MODE0");
+  if (!vid_ptr && Nv >= kXGroup && !(force0 && atoi(force0) == 1)) {
+    // dense form (mode 2): work items = groups of 4 videos x chunks of query tiles, several items per SM
+    const int groups = (Nv + kXGroup - 1) / kXGroup;
+    const int tiles = (M + kXRows - 1) / kXRows;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int chunks = 1;
+    while (chunks < tiles && (int64_t)groups * chunks < (int64_t)sms * 12) ++chunks;
+    p.tiles_per_chunk = (tiles + chunks - 1) / chunks;
+    p.tile_chunks = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.Nv_real = Nv;
+    p.Nv = groups * p.tile_chunks;
+    p.Npad = 128;
+    return launch_exact(2, p, D, T, (cudaStream_t)stream);
+  }
   return launch_exact(0, p, D, T, (cudaStream_t)stream);
 }

@@ -132,8 +132,8 @@ def compute_query2ctx_info(model, eval_dataset, opt, ctx_info):
     outs = [[] for _ in qs]
     for lo in range(0, qs[0].shape[0], chunk):
         pq = engine.prepare_queries([q[lo: lo + chunk] for q in qs], want_bf16=precision == "bf16")
-        if precision not in ("exact", "bf16", "fp16"):
-            raise ValueError(f"opt.precision must be 'exact', 'bf16' or 'fp16', got {precision!r}")
+        if precision not in ("exact", "bf16", "fp16", "shortcut"):
+            raise ValueError(f"opt.precision must be 'exact', 'bf16', 'fp16' or 'shortcut', got {precision!r}")
         if scoring == "frame":
             for o, (s, _) in zip(outs, engine.score_frame_head(pc, pq, precision)):
                 o.append(s)

@@ -749,8 +749,8 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
     // dense form (mode 2): work items = groups of 4 videos x chunks of query tiles, several items per SM
     const int groups = (Nv + kXGroup - 1) / kXGroup;
     const int tiles = (M + kXRows - 1) / kXRows;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int chunks = 1;
     while (chunks < tiles && (int64_t)groups * chunks < (int64_t)sms * 12) ++chunks;
     p.tiles_per_chunk = (tiles + chunks - 1) / chunks;

@@ -108,6 +108,8 @@ def test_config_streamed_corpus_equals_resident_corpus(ops):
     same = (i_bf == i_ex).all(dim=1)
     assert bool(same.all()), f"{int((~same).sum())} of {shape['Nq']} queries differ"
     assert torch.equal(s_bf, s_ex)
+    s_sc, i_sc = engine.rank_streamed(engine.iter_chunks(frames, mask, 4096), pqs, attn, K=100, precision="shortcut")
+    assert torch.equal(i_sc, i_ex) and torch.equal(s_sc, s_ex)
     pc = engine.prepare_corpus(frames, mask, attn, T=32, heads=("two_scale",), precisions=("exact",))
     s_all, i_all = engine.rank(pc, engine.prepare_queries(qs), K=100, head="two_scale", precision="exact")
     assert torch.equal(i_all, i_ex) and torch.equal(s_all, s_ex)

@@ -318,8 +318,8 @@ def main():
                          "pairs); shortcut (reported variant: no dense GEMM — exact clip scores for every pair "
                          "through 32 per-clip dots + window scan, approximate fp16 frame gather)")
     ap.add_argument("--candidates", type=int, default=K_CAND)
-    ap.add_argument("--variants-multi-gpu", action="store_true",
-                    help="also measure variants.shortcut when --gpus > 1 (default: single-GPU runs only)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the variants.shortcut measurement")
+    ap.add_argument("--variants-multi-gpu", action="store_true", help=argparse.SUPPRESS)   # accepted, now the default
     ap.add_argument("--e2e-steps", type=int, default=None, help="timed steps of the e2e leg (default max(3, steps/2))")
     args = ap.parse_args()
     if args.impl == "dkd_b200" and not args.profile:
@@ -537,7 +537,7 @@ def main():
     # ---- reported variant, same run / same box: the linearity-shortcut pass (exact clip scale for every pair, no dense
     # GEMM).  Not the headline: north_star specifies the dense bf16 GEMM.
     variants = None
-    if head == "two_scale" and args.operand != "shortcut" and not stream and (world == 1 or args.variants_multi_gpu):
+    if head == "two_scale" and args.operand != "shortcut" and not stream and not args.no_variants:
         for _ in range(2):
             step(qs, precision="shortcut")
         barrier()

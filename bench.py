@@ -153,51 +153,84 @@ def synth_c4(shape, device, shard_seed, nq=None):
 # ------------------------------------------------------------------------------------------------
 class CpuBaseline:
     """The oracle port of the reference's CPU eval loop on a bounded sample of the same workload:
-    `sample_queries` queries x the full corpus, all host threads.  Setup (synthetic features, random-init
-    encoders, corpus-side preparation) happens once in the constructor and is not timed."""
+    `sample_queries` queries x the full corpus, all host threads.  Setup (corpus-side preparation) happens once in
+    the constructor and is not timed.  `tensors` = (frames_by_branch, mask, queries_by_branch, attn_params) on the
+    host: the SAME encoded tensors the GPU arm scores (so the two results can be compared, `vs_oracle`); without
+    it (the --impl reference arm, which must not touch the GPU) the same synthetic workload is generated on the CPU."""
 
-    def __init__(self, shape, workload, max_queries, threads=None):
+    def __init__(self, shape, workload, max_queries, threads=None, tensors=None):
         from oracle import oracle as O
-        from dkd_b200.model import DLDKD
         self.O, self.shape, self.workload = O, shape, workload
         self.threads = threads or os.cpu_count()
         torch.set_num_threads(self.threads)
-        sub = dict(shape)
-        sub["Nq"] = max_queries
-        if workload == "c4_stream":
-            self.frames, self.mask, self.qs, params = synth_c4(sub, torch.device("cpu"), 0)
+        if tensors is not None:
+            self.frames, self.mask, self.qs, params = tensors
         else:
-            model, self.frames, self.mask, self.qs = synth_encoded(sub, torch.device("cpu"), 0, DLDKD)
-            params = model.attention_params()
+            from dkd_b200.model import DLDKD
+            sub = dict(shape)
+            sub["Nq"] = max_queries
+            if workload == "c4_stream":
+                self.frames, self.mask, self.qs, params = synth_c4(sub, torch.device("cpu"), 0)
+            else:
+                model, self.frames, self.mask, self.qs = synth_encoded(sub, torch.device("cpu"), 0, DLDKD)
+                params = model.attention_params()
         if workload != "tvr_frame":
             with torch.no_grad():
-                lengths = self.mask.sum(1).long()
-                self.props, self.keys, self.vals = [], [], []
-                for f, (kw, kb, vw, vb) in zip(self.frames, params):
-                    self.props.append(O.build_proposals(O.downsample_clips(f, lengths, shape["T"])))
-                    self.keys.append(torch.nn.functional.linear(f, kw, kb))
-                    self.vals.append(torch.nn.functional.linear(f, vw, vb))
+                self.props, self.keys, self.vals = O.two_scale_corpus(self.frames, self.mask, params, shape["T"])
 
-    def run(self, sample_queries):
-        """One timed pass -> dict for the JSON line."""
+    def run(self, sample_queries, keep=False):
+        """One timed pass -> dict for the JSON line (keep: also the fused matrix and the oracle's top-K ids)."""
         O = self.O
         qs = [q[:sample_queries] for q in self.qs]
         with torch.no_grad():
             t0 = time.perf_counter()
             if self.workload != "tvr_frame":
-                O.cpu_eval_two_scale(qs, self.props, self.keys, self.vals, self.mask, bsz=50, K=K_TOP)
+                fused, order = O.cpu_eval_two_scale(qs, self.props, self.keys, self.vals, self.mask, bsz=50, K=K_TOP)
             else:
-                O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
+                fused, order = O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
             dt = time.perf_counter() - t0
-        pairs = sample_queries * self.shape["Nv"]
-        return {"value": pairs / dt, "unit": "pairs/s", "cores": self.threads, "kind": "port",
-                "sample": f"{sample_queries} queries x {self.shape['Nv']} videos ({self.workload}, oracle/oracle.py "
-                          f"cpu_eval loop, batches of 50, torch {torch.__version__} CPU, {dt:.1f} s)",
-                "seconds": dt}
+        nv = self.mask.shape[0]
+        pairs = sample_queries * nv
+        out = {"value": pairs / dt, "unit": "pairs/s", "cores": self.threads, "kind": "port",
+               "sample": f"{sample_queries} queries x {nv} videos ({self.workload}, oracle/oracle.py "
+                         f"cpu_eval loop, batches of 50, torch {torch.__version__} CPU, {dt:.1f} s)",
+               "seconds": dt}
+        if keep:
+            out["_fused"], out["_order"] = fused, order
+        return out
+
+    def detail(self, n):
+        """Untimed: fused scores + key clips + fp32 key-clip tie mask of the first n queries (two-scale head), or the
+        fused scores with an empty tie mask (frame head)."""
+        O = self.O
+        qs = [q[:n] for q in self.qs]
+        with torch.no_grad():
+            if self.workload != "tvr_frame":
+                return O.two_scale_eval_detail(qs, self.props, self.keys, self.vals, self.mask, bsz=50)
+            fused, _ = O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
+            return dict(fused=fused, tie=np.zeros_like(fused, dtype=bool))
 
 
 def run_cpu_baseline(shape, workload, sample_queries, threads=None):
     return CpuBaseline(shape, workload, sample_queries, threads).run(sample_queries)
+
+
+def parity_vs_oracle(cpu, n, dense_exact, dense_approx, top_ids, id_base=0):
+    """The device results for the first n queries against the CPU oracle ON THE SAME TENSORS (north_star tolerances:
+    fused scores 1e-3 for the bf16 path, 5e-6 for the exact path, outside the oracle's own fp32 key-clip ties; top-K
+    ids identical up to swaps of oracle scores closer than 1e-5)."""
+    O = cpu.O
+    det = cpu.detail(n)
+    tie = det["tie"]
+    ref = det["fused"]
+    d_ex = np.abs(dense_exact.float().cpu().numpy() - ref)[~tie].max()
+    d_ap = np.abs(dense_approx.float().cpu().numpy() - ref)[~tie].max()
+    rk = O.compare_ranking(ref, tie, top_ids.cpu().numpy() - id_base, top_ids.shape[1])
+    ok = bool(d_ex <= 5e-6 and d_ap <= 1e-3 and rk["mismatches"] == 0)
+    return {"queries": int(n), "videos": int(ref.shape[1]), "max_abs_err_exact_path": float(d_ex),
+            "max_abs_err_timed_path": float(d_ap), "tol_exact": 5e-6, "tol_timed": 1e-3,
+            "key_clip_tie_pairs": int(tie.sum()), "ranking": rk, "ok": ok,
+            "what": "oracle/oracle.py two_scale_eval_detail (CPU fp32) on the encoded tensors the GPU scored"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,6 +452,10 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         prep_ms = e0.elapsed_time(e1)
+        attn_cpu = [tuple(t.detach().float().cpu() for t in p) for p in model.attention_params()]
+        host_tensors = None
+        if rank == 0 and not args.no_cpu_baseline and not args.profile:   # the oracle scores these very tensors
+            host_tensors = ([f.float().cpu() for f in frames], mask.float().cpu(), None, attn_cpu)
         del frames
         qs = [q.contiguous() for q in qs]
 
@@ -527,12 +564,20 @@ def main():
            "boundary": "encoded query vectors in pinned host memory -> engine.rank -> top-100 (score, id) in host memory; "
                        "copies on a side stream, overlapped with the neighbouring steps' kernels"}
 
-    # ---- parity of the timed result: bf16+rescore top-100 == exact fp32 path top-100 (first 512 queries)
+    # ---- parity of the timed result: bf16+rescore top-100 == exact fp32 path top-100, EVERY query (in slices of
+    # 2,048 to bound the exact path's dense temporaries)
+    same_ids = same_scores = True
     nchk = min(512, Nq)
-    s_ex, i_ex = step([q[:nchk] for q in qs], precision="exact")
-    parity = {"queries_checked": nchk,
-              "top100_ids_identical_to_exact_fp32": bool(torch.equal(i_ex, top_i[:nchk])),
-              "top100_scores_identical": bool(torch.equal(s_ex, top_s[:nchk]))}
+    n_par = nchk if stream else Nq          # streamed config: the all-exact pass over 125 k videos is bounded to 512 queries
+    for lo in range(0, n_par, 2048):
+        hi = min(lo + 2048, n_par)
+        s_ex, i_ex = step([q[lo:hi] for q in qs], precision="exact")
+        same_ids &= bool(torch.equal(i_ex, top_i[lo:hi]))
+        same_scores &= bool(torch.equal(s_ex, top_s[lo:hi]))
+    if n_par != nchk:
+        s_ex, i_ex = step([q[:nchk] for q in qs], precision="exact")
+    parity = {"queries_checked": n_par, "top100_ids_identical_to_exact_fp32": same_ids,
+              "top100_scores_identical": same_scores}
 
     # ---- reported variant, same run / same box: the linearity-shortcut pass (exact clip scale for every pair, no dense
     # GEMM).  Not the headline: north_star specifies the dense bf16 GEMM.
@@ -587,8 +632,8 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "fp16": "f16", "shortcut": "tf32x3"}[args.operand],
-                "data": "synthetic", "config": dict(cfg_common, parallelism=f"video-shard x{world}",
-                                                    candidates=args.candidates, rescoring="exact fp32"),
+                "data": "synthetic", "config": cfg_common,
+                "engine": {"parallelism": f"video-shard x{world}", "candidates": args.candidates, "rescoring": "exact fp32"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
@@ -597,10 +642,50 @@ def main():
                             "fallback_queries": engine.STATS["certify_fallback_queries"],
                             "note": "queries whose exact 100th score is within eps of the last candidate's approximate "
                                     "score are re-ranked by the all-exact path (all calls of this process)"}}
-        if not args.no_cpu_baseline and world >= 1:
-            nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
-            line["cpu_baseline"] = run_cpu_baseline(cpu_shape, args.workload, nq)
+        failed = not (parity["top100_ids_identical_to_exact_fp32"] and parity["top100_scores_identical"])
+        if not args.no_cpu_baseline:
+            # CPU leg: the oracle port of the reference's eval loop on the SAME encoded tensors (bounded sample of
+            # queries x the full corpus, >= ~20 s of CPU work), timed; then, untimed, the parity of the timed GPU
+            # result against it (parity.vs_oracle)
+            nq = args.cpu_sample_queries or (800 if head == "two_scale" else 3200)
+            nq = min(nq, Nq)
+            if stream:
+                nv_cpu = cpu_shape["Nv"]
+                tensors = ([f[:nv_cpu].float().cpu() for f in frames], mask[:nv_cpu].float().cpu(),
+                           [q[:nq].float().cpu() for q in qs], [tuple(t.float().cpu() for t in p) for p in attn])
+            else:
+                tensors = host_tensors[:2] + ([q[:nq].detach().float().cpu() for q in qs], host_tensors[3])
+            cpu = CpuBaseline(cpu_shape, args.workload, nq, tensors=tensors)
+            cpu.run(50)                                                   # warm the CPU kernels / allocator, untimed
+            line["cpu_baseline"] = cpu.run(nq)
+            nd = min(nq, 150)
+            qd = [q[:nd].contiguous() for q in qs]
+            if stream:   # the oracle's corpus slice, ranked by the same engine entry as the streamed chunks
+                pcs = engine.prepare_corpus([f[:nv_cpu] for f in frames], mask[:nv_cpu], attn, T=shape["T"],
+                                            heads=(head,), precisions=("exact", args.operand), id_base=rank * Nv)
+                pqd = engine.prepare_queries(qd)
+                _, ids_d = engine.rank(pcs, pqd, K=K_TOP, head=head, precision=args.operand, Kc=args.candidates)
+                id_base = rank * Nv
+            else:
+                pcs, pqd, id_base = pc, engine.prepare_queries(qd), rank * Nv
+                ids_d = top_i[:nd]                     # the TIMED result itself
+                if world > 1:                          # merged lists hold other ranks' videos: rank 0's local lists
+                    _, ids_d = engine.rank(pc, pqd, K=K_TOP, head=head, precision=args.operand, Kc=args.candidates)
+            if head == "two_scale":
+                dense_ex = engine.score_two_scale_head(pcs, pqd, "exact")[0]
+                dense_ap = engine.score_two_scale_head(pcs, pqd, args.operand)[0]
+            else:
+                fr_ex, fr_ap = engine.score_frame_head(pcs, pqd, "exact"), engine.score_frame_head(pcs, pqd, args.operand)
+                dense_ex = ops.fuse_scores(fr_ex[0][0], fr_ex[1][0], 0.7, 0.3)
+                dense_ap = ops.fuse_scores(fr_ap[0][0], fr_ap[1][0], 0.7, 0.3)
+            parity["vs_oracle"] = parity_vs_oracle(cpu, nd, dense_ex, dense_ap, ids_d, id_base)
+            failed = failed or not parity["vs_oracle"]["ok"]
+        if failed:
+            line["parity_failed"] = True
         print(json.dumps(line))
+        if failed:   # a fast result that differs from the reference's is not a result
+            sys.stdout.flush()
+            os._exit(1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,7 +1,7 @@
 """dkd_b200 — B200-native corpus retrieval scoring path of DL-DKD++ (HuiGuanLab/DL-DKD).
 
-The directory is named `dl-dkd_b200/`; import it as module `dkd_b200` through
-`__graft_entry__.load_package()` (a hyphen is not importable directly).
+The sources live in `dl-dkd_b200/`; the import name is `dkd_b200` (the `dkd_b200/` shim at the repository root
+points Python at this directory: a hyphen is not importable directly).
 
 Public surface (drop-in names of the reference):
     model.DLDKD                      encode_context / encode_query / get_sim_scores /

@@ -23,9 +23,8 @@
 //               (512 columns: 2 x 32 accumulator + 7 x 64 A ring)
 //   warp 13     B loader: one cp.async.bulk per video of its pre-packed clip planes (dkd_pack_clips_tf32: the
 //               shared-memory image of the B operand — tf32 hi / lo planes, K-major SWIZZLE_128B)
-#include <cstdlib>
-
 #include "dkd_umma.cuh"
+#include "dkd_scan.cuh"
 
 namespace dkd {
 
@@ -44,6 +43,7 @@ constexpr int kXTmemCols = 512;
 constexpr uint32_t kXRowPitch = 128;        // staged fp32 row of one K block; 16-byte chunk c of row r sits at
                                             // chunk c ^ ((r & 1) << 2): conflict-free cp.async writes and LDS.128 reads
 constexpr uint32_t kXSlotBytes = 32 * kXRowPitch;
+constexpr uint32_t kXScanScratch = 32 * kXRows * 4;   // 16 KB per scan group: the tile's dots, [clip][row]
 // per-stager-warp cp.async ring: kRing slots (kRing - 1 of the warp's K blocks in flight), 3 normally, 2 when D > 448
 
 struct ExactParams {
@@ -60,6 +60,7 @@ struct ExactParams {
   int Nv_real, tile_chunks, tiles_per_chunk;
 };
 constexpr int kXGroup = 4;                   // mode 2: videos sharing one staged A tile (UMMA N = 4 x 32 clips)
+constexpr bool kXPackedScan = false;         // window sums / products two at a time (add.rn.f32x2): see dkd_scan.cuh
 
 struct __align__(8) ExactCtl {
   uint64_t a_full[kXMaxAStages], a_empty[kXMaxAStages];
@@ -148,6 +149,7 @@ exact_umma_kernel(const ExactParams p) {
   constexpr int kDW = kMode == 0 ? 32 : 128;                    // accumulator columns per TMEM buffer
   constexpr int kScaleBufs = kMode == 2 ? kXGroup : 2;
   constexpr int kStageSets = kMode == 2 ? 1 : 2;                // stager warps per TMEM lane quarter
+  constexpr int kScanGroups = kMode == 2 ? 2 : (kMode == 0 ? 1 : 0);
   constexpr uint32_t kXACol0 = 2 * kDW;                         // first A-ring column
   constexpr int kXStages = (kXTmemCols - 2 * kDW) / 64;         // A ring stages: 7 / 4
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
@@ -160,7 +162,9 @@ exact_umma_kernel(const ExactParams p) {
   const uint32_t b_buf_bytes = kMode == 0 ? (uint32_t)num_kb * 2u * kXBPlane : 2u * (uint32_t)p.Npad * 128u;
   uint8_t* sB = smem;
   uint8_t* sS = sB + (size_t)(kMode == 0 ? p.b_bufs : kXBStages) * b_buf_bytes;   // [stager warp][slot][32 rows] x 128 B
-  ExactCtl* ctl = reinterpret_cast<ExactCtl*>(sS + (size_t)kXStageWarps * kXRing * kXSlotBytes);
+  // scan scratch (clip-window modes): per scan group 32 x 128 floats, column = tile row (two-phase scan, dkd_scan.cuh)
+  float* sD = reinterpret_cast<float*>(sS + (size_t)(4 * kStageSets) * kXRing * kXSlotBytes);
+  ExactCtl* ctl = reinterpret_cast<ExactCtl*>(reinterpret_cast<uint8_t*>(sD) + (size_t)kScanGroups * kXScanScratch);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bufs = (uint32_t)p.b_bufs;
 
@@ -446,37 +450,18 @@ exact_umma_kernel(const ExactParams p) {
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
           }
           const float* sc = s_scale[v];
-          float d[32], run[32];
+          float d[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
-          float bv[8];
-          int bi[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
-#pragma unroll
-          for (int w = 1; w <= 32; ++w) {
-            float scw[32];
-#pragma unroll
-            for (int s4 = 0; s4 + w <= 32; s4 += 4)
-              *reinterpret_cast<float4*>(&scw[s4]) = *reinterpret_cast<const float4*>(&sc[(w - 1) * 32 + s4]);
-#pragma unroll
-            for (int s = 0; s + w <= 32; ++s) {
-              run[s] = (w == 1) ? d[s] : __fadd_rn(run[s], d[s + w - 1]);
-              if (kT32 || s + w <= T) {
-                const int pi = kT32 ? ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s) : ((w - 1) * T - ((w - 1) * (w - 2)) / 2 + s);
-                const float val = __fmul_rn(run[s], scw[s]);
-                if (val > bv[s & 7]) { bv[s & 7] = val; bi[s & 7] = pi; }
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 1; k < 8; ++k)
-            if (better(bv[k], bi[k], bv[0], bi[0])) { bv[0] = bv[k]; bi[0] = bi[k]; }
+          float bv0;
+          int bi0;
+          if constexpr (kT32) window_scan_v2<kXPackedScan>(d, sc, sD + part * (kXScanScratch / 4) + quarter * 32 + lane, kXRows, bv0, bi0);
+          else window_scan_v1<false>(d, sc, T, bv0, bi0);
           const int vid = group * kXGroup + v;
           if (r < p.M && t0 + quarter * 32 + lane < count && vid < p.Nv_real) {
             const int64_t o = (int64_t)r * p.ld_out + vid;
-            p.out_max[o] = bv[0];
-            if (p.out_arg) p.out_arg[o] = bi[0];
+            p.out_max[o] = bv0;
+            if (p.out_arg) p.out_arg[o] = bi0;
           }
         }
       }
@@ -518,38 +503,19 @@ exact_umma_kernel(const ExactParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
-        float d[32], run[32];
+        float d[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
-        float bv[8];
-        int bi[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
-#pragma unroll
-        for (int w = 1; w <= 32; ++w) {
-          float scw[32];
-#pragma unroll
-          for (int s4 = 0; s4 + w <= 32; s4 += 4)
-            *reinterpret_cast<float4*>(&scw[s4]) = *reinterpret_cast<const float4*>(&sc[(w - 1) * 32 + s4]);
-#pragma unroll
-          for (int s = 0; s + w <= 32; ++s) {
-            run[s] = (w == 1) ? d[s] : __fadd_rn(run[s], d[s + w - 1]);
-            if (kT32 || s + w <= T) {
-              const int pi = kT32 ? ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2 + s) : ((w - 1) * T - ((w - 1) * (w - 2)) / 2 + s);
-              const float v = __fmul_rn(run[s], scw[s]);
-              if (v > bv[s & 7]) { bv[s & 7] = v; bi[s & 7] = pi; }
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 1; k < 8; ++k)
-          if (better(bv[k], bi[k], bv[0], bi[0])) { bv[0] = bv[k]; bi[0] = bi[k]; }
+        float bv0;
+        int bi0;
+        if constexpr (kT32) window_scan_v2<kXPackedScan>(d, sc, sD + quarter * 32 + lane, kXRows, bv0, bi0);
+        else window_scan_v1<false>(d, sc, T, bv0, bi0);
         const int r = t0 + quarter * 32 + lane;
         if (r < count) {
           const int64_t o = p.out_slot ? (int64_t)p.out_slot[e0 + r]
                                        : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n);
-          p.out_max[o] = bv[0];
-          if (p.out_arg) p.out_arg[o] = bi[0];
+          p.out_max[o] = bv0;
+          if (p.out_arg) p.out_arg[o] = bi0;
         }
       }
     }
@@ -668,15 +634,17 @@ extern "C" int dkd_pack_rows_tf32(const float* xn, int32_t Nv, int32_t R, int32_
 
 // shared launcher: mode 0 (clip windows) / mode 1 (rows max)
 static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStream_t st) {
-  { const char* e = getenv("DKD_EXACT_WAIT_NS"); p.wait_ns = e ? (unsigned)atoi(e) : 0u; }   // A/B on one box: no gain from sleeping
+  p.wait_ns = 0u;   // spin: sleeping between polls measured no gain
   int dev = 0, sms = 0, max_smem = 0;
   DKD_CUDA_TRY(cudaGetDevice(&dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_kb = D / kXKB;
   const int ring = D > 448 ? 2 : 3;
+  const int ring_warps = mode == 2 ? 4 : kXStageWarps;        // mode 2: one stager warp per TMEM lane quarter
+  const int scan_groups = mode == 2 ? 2 : (mode == 0 ? 1 : 0);
   const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 16384 /* static shared, largest mode */ +
-                       (size_t)kXStageWarps * ring * kXSlotBytes;
+                       (size_t)ring_warps * ring * kXSlotBytes + (size_t)scan_groups * kXScanScratch;
   size_t b_total;
   if (mode == 0) {
     const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
@@ -744,8 +712,7 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
   p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
   p.vid_ptr = vid_ptr; p.vid_cnt = vid_cnt; p.q_list = q_list; p.out_slot = out_slot;
-  const char* force0 = getenv("DKD_EXACT_MODE0");
-  if (!vid_ptr && Nv >= kXGroup && !(force0 && atoi(force0) == 1)) {
+  if (!vid_ptr && Nv >= kXGroup) {
     // dense form (mode 2): work items = groups of 4 videos x chunks of query tiles, several items per SM
     const int groups = (Nv + kXGroup - 1) / kXGroup;
     const int tiles = (M + kXRows - 1) / kXRows;

@@ -22,8 +22,6 @@
 //
 // Operand layout: K-major, 128-byte swizzle (TMA SWIZZLE_128B <-> UMMA SWIZZLE_128B descriptors),
 // one K block = 64 bf16 = 128 B per row, 8-row groups 1024 B apart.
-#include <cstdlib>
-
 #include "dkd_umma.cuh"
 
 namespace dkd {
@@ -84,8 +82,6 @@ struct GemmParams {
   float tau;
   int flag_words;     // words per query row = ceil(Nv / 32)
   int f16;            // operands are IEEE half instead of bf16 (same 2-byte layout, same MMA kind::f16 rate)
-  int debug_flags;    // DKD_GEMM_DEBUG env: 1 = skip epilogue math, 2 = always load corpus tile 0,
-                      // 4 = MMA does not wait for the corpus ring, 8 = no corpus TMA at all (timing experiments)
   int64_t ld_out;
 };
 
@@ -162,9 +158,8 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int v1 = min(v0 + p.video_chunk, p.Nv);
         for (int v = v0; v < v1; ++v) {
           for (int t = 0; t < tiles_per_video; ++t) {
-            const int row = (p.debug_flags & 2) ? 0 : v * p.R + t * p.block_n;
+            const int row = v * p.R + t * p.block_n;
             for (int kb = 0; kb < num_kb; kb += kbs) {
-              if (p.debug_flags & 8) continue;
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               uint8_t* dst = smem_b + (size_t)stage * b_stage_bytes;
               if (kCta == 1) {
@@ -261,7 +256,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               adesc += a_kb_step;
               bdesc += b_kb_step;
               // absorb the wait for the NEXT stage behind the MMAs just queued
-              if (j == 0 && steps_left > 0 && !(p.debug_flags & 16)) {
+              if (j == 0 && steps_left > 0) {
                 mbar_wait(&ctl->full[nstage], nphase);
                 have_full = true;
               }
@@ -304,19 +299,17 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           // All TMEM loads of this warp's column half are issued back to back and waited for ONCE:
           // tcgen05.ld latency is long while the tensor pipe is busy, so it is paid per tile, not per chunk.
           uint32_t r[96];
-          if (!(p.debug_flags & 1)) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const int c = c_lo + 2 * i;
-              if (c + 1 < c_hi) tmem_ld32_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
-              else if (c < c_hi) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
-            }
-            tmem_ld_wait();
+          for (int i = 0; i < 3; ++i) {
+            const int c = c_lo + 2 * i;
+            if (c + 1 < c_hi) tmem_ld32_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+            else if (c < c_hi) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+          }
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const int c = c_lo + i;
-              if (c < c_hi) top2_chunk<kHasMask>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
-            }
+          for (int i = 0; i < 6; ++i) {
+            const int c = c_lo + i;
+            if (c < c_hi) top2_chunk<kHasMask>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
           }
           tc_fence_before();
           __syncwarp();
@@ -452,19 +445,16 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
   // CTA pairs (cta_group::2) whenever the shapes allow: two query tiles per pair, corpus tile split in
-  // halves of a multiple of 8 rows.  DKD_GEMM_CTA=1 forces the single-CTA kernel (A/B measurements).
-  int cta = (Mpad % (2 * kBlockM) == 0 && (block_n / 2) % 8 == 0 && sms >= 2) ? 2 : 1;
-  { const char* e = getenv("DKD_GEMM_CTA"); if (e && atoi(e) == 1) cta = 1; }
+  // halves of a multiple of 8 rows.
+  const int cta = (Mpad % (2 * kBlockM) == 0 && (block_n / 2) % 8 == 0 && sms >= 2) ? 2 : 1;
 
   const int num_kb = D / kBlockK;
   const size_t a_bytes = (size_t)num_kb * kBlockM * kBlockK * 2;
   // K blocks per ring stage.  Every stage costs one full/empty handshake on the single issuing thread,
   // which is the scarce resource: CTA pairs (half-size stages) take 3 K blocks per stage when D allows,
-  // measured 1.38 PF vs 1.05 PF with 1 (profiles/r1_gemm_variants.md).  DKD_GEMM_KBS overrides.
+  // measured 1.38 PF vs 1.05 PF with 1 (profiles/r1_gemm_variants.md).
   int kbs = 1;
   if (cta == 2) kbs = (num_kb % 3 == 0) ? 3 : ((num_kb % 2 == 0) ? 2 : 1);
-  { const char* e = getenv("DKD_GEMM_KBS"); if (e && atoi(e) > 0) kbs = atoi(e); }
-  if (kbs < 1 || num_kb % kbs != 0) kbs = 1;
   const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2 * kbs;
   const size_t fixed = a_bytes + sizeof(SmemCtl) + 1024 /* alignment slack */ + 256;
   if ((size_t)max_smem < fixed + 2 * b_stage) return DKD_ERR_SHAPE;
@@ -481,7 +471,6 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   GemmParams p{};
   p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
   p.f16 = f16 ? 1 : 0;
-  { const char* e = getenv("DKD_GEMM_DEBUG"); p.debug_flags = e ? atoi(e) : 0; }
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
   // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1

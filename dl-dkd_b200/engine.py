@@ -60,6 +60,12 @@ class PreparedCorpus:
     lengths: torch.Tensor          # (Nv,) int32
     branches: List[BranchData] = field(default_factory=list)
     heads: tuple = ("frame", "two_scale")
+    # rows per video as the tcgen05 GEMM sees them: the kernel needs R % 16 == 0, so frames / proposals are padded
+    # with masked zero rows (frame head: Lg >= L, mask_g (Nv, Lg); two-scale head: Pg >= P, prop_mask (Nv, Pg) | None)
+    Lg: int = 0
+    mask_g: Optional[torch.Tensor] = None
+    Pg: int = 0
+    prop_mask: Optional[torch.Tensor] = None
 
     @property
     def P(self):
@@ -89,9 +95,27 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
     mask_u8 = (mask > 0).to(torch.uint8).contiguous()
     lengths = mask_u8.sum(dim=1).to(torch.int32).contiguous()
     pc = PreparedCorpus(Nv=Nv, L=L, D=D, T=T, id_base=id_base, mask_u8=mask_u8, lengths=lengths, heads=tuple(heads))
+    P = ops.num_proposals(T)
+    pc.Lg, pc.Pg = ops.round_up(L, 16), ops.round_up(P, 16)
+    pc.mask_g = mask_u8
+    if pc.Lg != L:
+        pc.mask_g = torch.zeros((Nv, pc.Lg), dtype=torch.uint8, device=f0.device)
+        pc.mask_g[:, :L] = mask_u8
+    if pc.Pg != P:
+        pc.prop_mask = torch.zeros((Nv, pc.Pg), dtype=torch.uint8, device=f0.device)
+        pc.prop_mask[:, :P] = 1
     if Nv == 0:  # an empty shard (more ranks than videos): nothing to prepare, rank() returns padding
         pc.branches = [BranchData() for _ in frames_by_branch]
         return pc
+
+    def pad_rows(t, R, Rg):
+        """(Nv * R, D) GEMM operand -> (Nv * Rg, D) with zero rows appended to every video (masked in the kernel)."""
+        if t is None or Rg == R:
+            return t
+        out = torch.zeros((Nv, Rg, D), dtype=t.dtype, device=t.device)
+        out[:, :R] = t.view(Nv, R, D)
+        return out.view(Nv * Rg, D)
+
     for bi, fr in enumerate(frames_by_branch):
         fr = fr.contiguous().float()
         bd = BranchData()
@@ -101,8 +125,8 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
                                      want_bf16="bf16" in precisions, want_f16="fp16" in precisions)
             fn, fb, fh = out if len(out) == 3 else (out[0], out[1], None)
             bd.frames_n = None if fn is None else fn.view(Nv, L, D)
-            bd.frames_b = fb
-            bd.frames_h = fh
+            bd.frames_b = pad_rows(fb, L, pc.Lg)
+            bd.frames_h = pad_rows(fh, L, pc.Lg)
             if bd.frames_n is not None and D % 32 == 0:
                 bd.frame_planes = ops.pack_rows(bd.frames_n)
         if "two_scale" in heads:
@@ -112,10 +136,10 @@ def prepare_corpus(frames_by_branch, mask, attn_params=None, T=ops.T_CLIPS, head
             bd.clips = ops.downsample_clips(fr, lengths, T)
             bd.clip_planes = ops.pack_clips(bd.clips)
             pb, ps, _ = ops.build_proposals(bd.clips, want_bf16="bf16" in precisions, want_scale=True)
-            bd.prop_b = None if pb is None else pb.view(-1, D)
+            bd.prop_b = None if pb is None else pad_rows(pb.view(-1, D), P, pc.Pg)
             bd.prop_scale = ps
             if "fp16" in precisions:
-                bd.prop_h = ops.build_proposals_f16(bd.clips)[0].view(-1, D)
+                bd.prop_h = pad_rows(ops.build_proposals_f16(bd.clips)[0].view(-1, D), P, pc.Pg)
             # W_k / W_v projections: plain library GEMMs in corpus preparation
             key = F.linear(fr, kw, kb).contiguous()
             val = F.linear(fr, vw, vb).contiguous()
@@ -171,9 +195,9 @@ def score_frame_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exact",
         if precision == "exact":
             s, a = _exact_rows(bd, qn, pc)
         elif precision == "fp16":
-            s, a = ops.score_max_bf16(qh, pq.M, bd.frames_h, pc.Nv, pc.L, pc.mask_u8)
+            s, a = ops.score_max_bf16(qh, pq.M, bd.frames_h, pc.Nv, pc.Lg, pc.mask_g)
         else:
-            s, a = ops.score_max_bf16(qb, pq.M, bd.frames_b, pc.Nv, pc.L, pc.mask_u8)
+            s, a = ops.score_max_bf16(qb, pq.M, bd.frames_b, pc.Nv, pc.Lg, pc.mask_g)
         out.append((s, a))
     return out
 
@@ -213,11 +237,11 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
             else:
                 prop = bd.prop_b
             if tau > 0:
-                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.P, flag_tau=tau)
+                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.Pg, mask=pc.prop_mask, flag_tau=tau)
                 vb, ql, vc, slot = ops.select_flagged(flags, pc.Nv)
                 ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=(vb, ql, vc), scatter=(slot, s_clip, k_clip))
             else:
-                s_clip, k_clip = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.P)
+                s_clip, k_clip = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.Pg, mask=pc.prop_mask)
             q, tab = qh, bd.table_h
         wb = wbs[bi] if nb == 2 else 1.0
         fused, fr = ops.frame_fuse(q, tab, s_clip, k_clip, w_clip, w_frame, wb, fused=fused, accumulate=bi > 0,
@@ -232,24 +256,72 @@ CERT_EPS_F16 = 2.5e-4
 STATS = {"certify_fallback_queries": 0, "certify_checked_queries": 0}
 
 
+class PendingCertificate:
+    """The device-side outcome of one rank() call's candidate certificate, to be looked at later (certify="deferred"):
+    `count` reaches pinned host memory through an asynchronous copy, `resolve()` waits for it and — only if some query
+    failed the check — re-ranks those queries by the all-exact path and patches the returned tensors in place."""
+
+    def __init__(self, pc, pq, unsure, out_s, out_i, args):
+        self.pc, self.pq, self.unsure, self.out_s, self.out_i, self.args = pc, pq, unsure, out_s, out_i, args
+        self.host = torch.empty((1,), dtype=torch.int32).pin_memory()
+        self.host.copy_(unsure.sum(dtype=torch.int32).reshape(1), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def resolve(self):
+        self.event.synchronize()
+        return _apply_fallback(self.pc, self.pq, self.unsure, int(self.host[0]), self.out_s, self.out_i, self.args)
+
+
+PENDING: List[PendingCertificate] = []
+
+
+def finish():
+    """Resolve every deferred certificate (see rank(certify="deferred")).  Returns the number of queries that had to
+    be re-ranked by the exact path."""
+    n = 0
+    while PENDING:
+        n += PENDING.pop(0).resolve()
+    return n
+
+
+def _apply_fallback(pc, pq, unsure, n_unsure, out_s, out_i, args):
+    STATS["certify_checked_queries"] += pq.M
+    STATS["certify_fallback_queries"] += n_unsure
+    if n_unsure:
+        nb = len(pc.branches)
+        idx = unsure.nonzero().squeeze(1)
+        sub = PreparedQueries(M=n_unsure, Mpad=ops.round_up(n_unsure, 256), qn=[q[idx].contiguous() for q in pq.qn],
+                              qb=[None] * nb, qh=[None] * nb)
+        es, ei = rank(pc, sub, precision="exact", **args)
+        out_s[idx] = es
+        out_i[idx] = ei
+    return n_unsure
+
+
 def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", precision="bf16", rescore=True,
-         Kc=128, w_clip=0.7, w_frame=0.3, tau=None, certify=True):
-    """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score.
+         Kc=128, w_clip=0.7, w_frame=0.3, tau=None, certify=True, return_dense=False):
+    """Per-query top-K (scores (M,K) fp32, global video ids (M,K) int32) of the fused score
+    [+ the dense (M, Nv) fused matrix of the scoring pass when return_dense].
 
     precision="bf16" + rescore: bf16 GEMM scores pick Kc >= K candidates per query, the exact fp32
     kernels re-score them, the K best survive.  certify: a query's list is accepted only if its exact K-th
     score exceeds the approximate score of the last candidate by more than CERT_EPS — every non-candidate
     scores at most that approximate value, so (approximation error <= CERT_EPS) none of them can belong in the
     top-K.  The few queries that fail the check are re-ranked by the all-exact path, which makes the result equal
-    to precision="exact" for every query instead of "for every query we tested" (one scalar device->host read per
-    call; STATS counts the fallbacks).
+    to precision="exact" for every query instead of "for every query we tested".
+      certify=True        the check is read back immediately (one scalar device->host read per call);
+      certify="deferred"  no host synchronisation: the outcome is queued in PENDING and engine.finish() — called by
+                          the consumer before it reads the lists — applies the (rare) exact re-rank in place.  This
+                          form can be captured in a CUDA graph.
     """
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
     if pq.M == 0 or pc.Nv == 0:  # no queries / empty shard: K columns of padding (score -inf, id -1), like dkd_topk
         dev = pc.mask_u8.device
-        return (torch.full((pq.M, K), float("-inf"), dtype=torch.float32, device=dev),
-                torch.full((pq.M, K), -1, dtype=torch.int32, device=dev))
+        out = (torch.full((pq.M, K), float("-inf"), dtype=torch.float32, device=dev),
+               torch.full((pq.M, K), -1, dtype=torch.int32, device=dev))
+        return out + (torch.empty((pq.M, pc.Nv), dtype=torch.float32, device=dev),) if return_dense else out
     per = None
     if head == "frame":
         if precision == "shortcut":
@@ -258,8 +330,9 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
         fused = sc[0][0] if nb == 1 else ops.fuse_scores(sc[0][0], sc[1][0], wbs[0], wbs[1])
     else:
         fused, per = score_two_scale_head(pc, pq, precision, w_clip, w_frame, tau=tau)
+    extra = (fused,) if return_dense else ()
     if precision == "exact" or not rescore:
-        return ops.topk(fused, K, pc.id_base)
+        return ops.topk(fused, K, pc.id_base) + extra
     Kc = max(Kc, K)
     approx_s, cand = ops.topk(fused, Kc, pc.id_base)
     csr = ops.candidates_to_csr(cand, pc.Nv, pc.id_base)
@@ -281,17 +354,12 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     out_s, out_i = ops.sort_candidates(cand_scores, cand, K)
     if certify and Kc < pc.Nv:
         unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + (CERT_EPS if precision == "bf16" else CERT_EPS_F16)
-        n_unsure = int(unsure.sum())
-        STATS["certify_checked_queries"] += pq.M
-        STATS["certify_fallback_queries"] += n_unsure
-        if n_unsure:
-            idx = unsure.nonzero().squeeze(1)
-            sub = PreparedQueries(M=n_unsure, Mpad=ops.round_up(n_unsure, 256), qn=[q[idx].contiguous() for q in pq.qn],
-                                  qb=[None] * nb, qh=[None] * nb)
-            es, ei = rank(pc, sub, K=K, head=head, precision="exact", w_clip=w_clip, w_frame=w_frame)
-            out_s[idx] = es
-            out_i[idx] = ei
-    return out_s, out_i
+        args = dict(K=K, head=head, w_clip=w_clip, w_frame=w_frame)
+        if certify == "deferred":
+            PENDING.append(PendingCertificate(pc, pq, unsure, out_s, out_i, args))
+        else:
+            _apply_fallback(pc, pq, unsure, int(unsure.sum()), out_s, out_i, args)
+    return (out_s, out_i) + extra
 
 
 def shard_range(Nv: int, rank_: int, world: int):

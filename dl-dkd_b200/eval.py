@@ -43,18 +43,29 @@ def _pad_stack(seqs):
 
 
 def collate_frame_val(data):
-    feats, idxs, ids = zip(*data)
+    """method/data_provider.py:139-148: items (feat, idx, id) -> (videos, mask, idxs, ids); items that also carry
+    teacher features (feat, teacher_feat, idx, id) -> (videos, teacher_videos, mask, idxs, ids)."""
+    if len(data[0]) == 3:
+        feats, idxs, ids = zip(*data)
+        videos, mask = _pad_stack(feats)
+        return videos, mask, idxs, ids
+    feats, teacher, idxs, ids = zip(*data)
     videos, mask = _pad_stack(feats)
-    return videos, mask, idxs, ids
+    teacher_videos, _ = _pad_stack(teacher)
+    return videos, teacher_videos, mask, idxs, ids
 
 
 def collate_text_val(data):
-    """Each batch is re-ordered by caption length, longest first (method/data_provider.py:153-154);
-    query_metas carries the resulting row order."""
+    """Each batch is re-ordered by caption length, longest first (method/data_provider.py:152-170);
+    query_metas carries the resulting row order.  4-tuple items carry one teacher (CLIP) text vector each."""
     data = sorted(data, key=lambda x: len(x[0]), reverse=True)
-    feats, idxs, ids = zip(*data)
+    if len(data[0]) == 3:
+        feats, idxs, ids = zip(*data)
+        target, mask = _pad_stack(feats)
+        return target, mask, idxs, ids
+    feats, teacher, idxs, ids = zip(*data)
     target, mask = _pad_stack(feats)
-    return target, mask, idxs, ids
+    return target, torch.cat([t.reshape(1, -1) for t in teacher], dim=0), mask, idxs, ids
 
 
 def _cat_padded(tensors):
@@ -75,17 +86,24 @@ def _cat_padded(tensors):
 
 def compute_context_info(model, eval_dataset, opt):
     """Encode the whole corpus and prepare it on the device.  Returns the reference's dict
-    (video_metas, inher_frame_feat, explore_frame_feat, teacher_frame_feat=None, video_mask) plus
-    `prepared`: the engine.PreparedCorpus used by compute_query2ctx_info / rank_queries."""
+    (video_metas, inher_frame_feat, explore_frame_feat, teacher_frame_feat, video_mask) plus
+    `prepared`: the engine.PreparedCorpus used by compute_query2ctx_info / rank_queries.
+
+    Datasets whose items carry teacher (CLIP) frame features (5-field batches, method/eval.py:129-132): the teacher
+    features are scored raw, like DLDKD.forward does (method/model.py:113-114), so teacher_frame_feat is their padded
+    concatenation.  (The reference passes them to encode_context as a third argument, which its own two-argument
+    encode_context, method/model.py:215, rejects with a TypeError.)"""
     model.eval()
     loader = DataLoader(eval_dataset, collate_fn=collate_frame_val, batch_size=opt.eval_context_bsz,
                         num_workers=_opt(opt, "num_workers", 0), shuffle=False, pin_memory=_opt(opt, "pin_memory", False))
-    metas, inher, explore, masks = [], [], [], []
+    metas, inher, explore, teacher, masks = [], [], [], [], []
     with torch.no_grad():
         for batch in loader:
             metas.extend(batch[-1])
             feat = batch[0].to(opt.device, non_blocking=True)
-            mask = batch[1].to(opt.device, non_blocking=True)
+            mask = batch[-3].to(opt.device, non_blocking=True)
+            if len(batch) == 5:
+                teacher.append(batch[1].to(opt.device, non_blocking=True))
             fi, fe = model.encode_context(feat, mask)
             inher.append(fi)
             explore.append(fe)
@@ -98,74 +116,89 @@ def compute_context_info(model, eval_dataset, opt):
         prepared = model.prepare_context(inher, explore, video_mask, heads=(scoring,),
                                          precisions=("exact",) if precision == "exact" else ("exact", precision),
                                          id_base=_opt(opt, "id_base", 0))
-    return dict(video_metas=metas, inher_frame_feat=inher, explore_frame_feat=explore, teacher_frame_feat=None,
-                video_mask=video_mask, prepared=prepared)
+    return dict(video_metas=metas, inher_frame_feat=inher, explore_frame_feat=explore,
+                teacher_frame_feat=_cat_padded(teacher), video_mask=video_mask, prepared=prepared)
 
 
 def _encode_all_queries(model, eval_dataset, opt):
     loader = DataLoader(eval_dataset, collate_fn=collate_text_val, batch_size=opt.eval_query_bsz,
                         num_workers=_opt(opt, "num_workers", 0), shuffle=False, pin_memory=_opt(opt, "pin_memory", False))
-    metas, qi, qe = [], [], []
+    metas, qi, qe, qt = [], [], [], []
     with torch.no_grad():
         for batch in loader:
             metas.extend(batch[-1])
-            a, b = model.encode_query(batch[0].to(opt.device, non_blocking=True), batch[1].to(opt.device, non_blocking=True))
+            a, b = model.encode_query(batch[0].to(opt.device, non_blocking=True), batch[-3].to(opt.device, non_blocking=True))
             qi.append(a)
             qe.append(b)
+            if len(batch) == 5:
+                qt.append(batch[1].to(opt.device, non_blocking=True))
     qs = [torch.cat(qi, dim=0)]
     if model.double_branch:
         qs.append(torch.cat(qe, dim=0))
-    return qs, metas
+    return qs, metas, (torch.cat(qt, dim=0) if qt else None)
+
+
+_PRECISIONS = ("exact", "bf16", "fp16", "shortcut")
 
 
 def compute_query2ctx_info(model, eval_dataset, opt, ctx_info):
-    """Score every query against the whole corpus.  Returns (inher_scores, explore_scores | None, None,
-    query_metas) with numpy float32 (Nq, Nv) matrices in DataLoader row order, like the reference.
+    """Score every query against the whole corpus.  Returns (inher_scores, explore_scores | None, teacher_scores |
+    None, query_metas) with numpy float32 (Nq, Nv) matrices in DataLoader row order, like the reference.
     With opt.scoring == "two_scale" the matrices are the per-branch two-scale scores
-    (w_clip * clip + w_frame * frame)."""
+    (w_clip * clip + w_frame * frame).  This is the reference's interface and, like it, ends in a dense
+    device->host copy; the ranking-only hot path is rank_queries / eval_epoch(opt.precision != "exact")."""
     model.eval()
     pc = ctx_info["prepared"]
-    qs, metas = _encode_all_queries(model, eval_dataset, opt)
+    qs, metas, qt = _encode_all_queries(model, eval_dataset, opt)
     precision = _opt(opt, "precision", "exact")
     scoring = _opt(opt, "scoring", "frame")
+    if precision not in _PRECISIONS:
+        raise ValueError(f"opt.precision must be one of {_PRECISIONS}, got {precision!r}")
     chunk = int(_opt(opt, "query_chunk", 16384))
     outs = [[] for _ in qs]
     for lo in range(0, qs[0].shape[0], chunk):
         pq = engine.prepare_queries([q[lo: lo + chunk] for q in qs], want_bf16=precision == "bf16")
-        if precision not in ("exact", "bf16", "fp16", "shortcut"):
-            raise ValueError(f"opt.precision must be 'exact', 'bf16', 'fp16' or 'shortcut', got {precision!r}")
         if scoring == "frame":
             for o, (s, _) in zip(outs, engine.score_frame_head(pc, pq, precision)):
                 o.append(s)
         else:
             for bi in range(len(qs)):  # per-branch two-scale score = fused with branch weight 1
                 sub = engine.PreparedCorpus(Nv=pc.Nv, L=pc.L, D=pc.D, T=pc.T, id_base=pc.id_base, mask_u8=pc.mask_u8,
-                                            lengths=pc.lengths, branches=[pc.branches[bi]], heads=pc.heads)
+                                            lengths=pc.lengths, branches=[pc.branches[bi]], heads=pc.heads,
+                                            Lg=pc.Lg, mask_g=pc.mask_g, Pg=pc.Pg, prop_mask=pc.prop_mask)
                 subq = engine.PreparedQueries(M=pq.M, Mpad=pq.Mpad, qn=[pq.qn[bi]], qb=[pq.qb[bi]], qh=[pq.qh[bi]])
                 f, _ = engine.score_two_scale_head(sub, subq, precision, model.clip_scale_w, model.frame_scale_w)
                 outs[bi].append(f)
     inher = torch.cat(outs[0], dim=0).cpu().numpy().copy()
     explore = torch.cat(outs[1], dim=0).cpu().numpy().copy() if model.double_branch else None
-    return inher, explore, None, metas
+    teacher = None
+    if ctx_info.get("teacher_frame_feat") is not None and qt is not None:   # method/eval.py:198-202
+        teacher = model.get_sim_scores(qt, ctx_info["teacher_frame_feat"], ctx_info["video_mask"],
+                                       want_rows=False)[0].cpu().numpy().copy()
+    return inher, explore, teacher, metas
 
 
-def rank_queries(model, eval_dataset, opt, ctx_info, K=100):
+def rank_queries(model, eval_dataset, opt, ctx_info, K=100, return_dense=False):
     """The hot path: per-query top-K (fused score desc) without materialising anything on the host.
-    Returns (scores (Nq, K) fp32 CUDA, ids (Nq, K) int32 CUDA, query_metas)."""
+    Returns (scores (Nq, K) fp32 CUDA, ids (Nq, K) int32 CUDA, query_metas) [+ the dense (Nq, Nv) fused device
+    matrix of the scoring pass when return_dense].  No host synchronisation inside: the candidate certificates of
+    the tcgen05 path are resolved once at the end (engine.finish)."""
     model.eval()
     pc = ctx_info["prepared"]
-    qs, metas = _encode_all_queries(model, eval_dataset, opt)
+    qs, metas, _ = _encode_all_queries(model, eval_dataset, opt)
     precision = _opt(opt, "precision", "exact")
     scoring = _opt(opt, "scoring", "frame")
+    if precision not in _PRECISIONS:
+        raise ValueError(f"opt.precision must be one of {_PRECISIONS}, got {precision!r}")
     chunk = int(_opt(opt, "query_chunk", 16384))
-    ss, ii = [], []
+    outs = []
     for lo in range(0, qs[0].shape[0], chunk):
         pq = engine.prepare_queries([q[lo: lo + chunk] for q in qs], want_bf16=precision == "bf16")
-        s, i = engine.rank(pc, pq, K=K, head=scoring, precision=precision, w_clip=model.clip_scale_w,
-                           w_frame=model.frame_scale_w)
-        ss.append(s)
-        ii.append(i)
-    return torch.cat(ss), torch.cat(ii), metas
+        outs.append(engine.rank(pc, pq, K=K, head=scoring, precision=precision, w_clip=model.clip_scale_w,
+                                w_frame=model.frame_scale_w, certify="deferred", return_dense=return_dense))
+    engine.finish()
+    res = tuple(torch.cat([o[j] for o in outs]) for j in range(len(outs[0])))
+    return res[:2] + (metas,) + res[2:]
 
 
 def get_gt(video_metas, query_metas):
@@ -239,20 +272,81 @@ def recall_from_topk(top_ids, t2v_gt, ks=(1, 5, 10, 100)):
     return tuple(out)
 
 
+def metrics_from_ranking(top_ids, dense, t2v_gt, id_base=0):
+    """(r1, r5, r10, r100, medr, meanr, mAP) of a device ranking, integer work on the device:
+    the GT rank comes from the ranked top-K id lists where a GT video is in them (exact: these are the rescored
+    lists) and from dkd_rank_of_gt on the dense fused scores of the scoring pass otherwise (for the tcgen05 path
+    those are the approximate scores, |d| <= 1e-3: only ranks beyond K, i.e. medr / meanr / mAP tails, see them;
+    R@K for K <= top-K never does)."""
+    M, K = top_ids.shape
+    dev = top_ids.device
+    ptr, gts = _gt_csr(t2v_gt, M)
+    ptr1, first = _gt_csr(t2v_gt, M, first_only=True)
+    ptr, gts, ptr1, first = ptr.to(dev), gts.to(dev), ptr1.to(dev), first.to(dev)
+
+    def ranks(p, g):
+        r_dense = ops.rank_of_gt(dense, p, g).long()
+        cnt = (p[1:] - p[:-1]).long()
+        owner = torch.repeat_interleave(torch.arange(M, device=dev), cnt)              # query of every GT entry
+        hit = top_ids[owner].long() == (g.long() + id_base).unsqueeze(1)               # (n_gt, K)
+        pos = torch.where(hit.any(1), hit.float().argmax(1) + 1, torch.full_like(owner, K + 1))
+        best = torch.full((M,), K + 1, dtype=torch.long, device=dev).scatter_reduce(0, owner, pos, "amin")
+        return torch.where(best <= K, best, torch.maximum(r_dense, torch.full_like(r_dense, K + 1))).cpu().numpy()
+
+    r = ranks(ptr, gts)
+    rk = [100.0 * np.count_nonzero(r <= k) / M for k in (1, 5, 10, 100)]
+    r1 = ranks(ptr1, first)
+    return (rk[0], rk[1], rk[2], rk[3], np.median(r), r.mean(), float(np.mean(1.0 / r1)))
+
+
+def _log_perf(m):
+    logger.info(" * Text to Video:")
+    logger.info(" * r_1_5_10_100: {}".format([round(x, 1) for x in m[:4]]))
+    logger.info(" * recall sum: {}".format(round(sum(m[:4]), 1)))
+    logger.info(" * mAP: {}".format(round(m[6], 4)))
+
+
 def eval_epoch(model, val_video_dataset, val_text_dataset, opt, test=False):
-    """R@1 + R@5 + R@10 + R@100 of the fused score (method/eval.py:237-263)."""
+    """R@1 + R@5 + R@10 + R@100 of the fused score (method/eval.py:237-263).
+
+    opt.precision == "exact" (default): the reference's flow — dense per-branch matrices on the host, the three
+    cal_perf reports (inheritance, exploration, fused).
+    opt.precision in ("bf16", "fp16", "shortcut"): the hot path — engine.rank on the device (tcgen05 scoring +
+    exact rescoring, top-100 identical to the exact path), R@K and the rank statistics computed on the device from
+    the ranked lists; nothing of size Nq x Nv crosses to the host.  Only the fused report is produced
+    (opt.per_branch_metrics = True adds the two single-branch reports at the cost of two more ranking passes)."""
     model.eval()
+    precision = _opt(opt, "precision", "exact")
+    if precision == "exact":
+        with torch.no_grad():
+            ctx = compute_context_info(model, val_video_dataset, opt)
+            inher, explore, _, query_metas = compute_query2ctx_info(model, val_text_dataset, opt, ctx)
+        _, t2v_gt = get_gt(ctx["video_metas"], query_metas)
+        if _opt(opt, "double_branch", model.double_branch) and explore is not None:
+            cal_perf(-1 * inher, t2v_gt, test)
+            cal_perf(-1 * explore, t2v_gt, test)
+            a = torch.from_numpy(inher).to(opt.device)
+            b = torch.from_numpy(explore).to(opt.device)
+            fused = ops.fuse_scores(a, b, 0.7, 0.3).cpu().numpy()
+            r = cal_perf(-1 * fused, t2v_gt, test)
+        else:
+            r = cal_perf(-1 * inher, t2v_gt, test)
+        return r[0] + r[1] + r[2] + r[3]
     with torch.no_grad():
         ctx = compute_context_info(model, val_video_dataset, opt)
-        inher, explore, _, query_metas = compute_query2ctx_info(model, val_text_dataset, opt, ctx)
+        _, top_ids, query_metas, dense = rank_queries(model, val_text_dataset, opt, ctx, K=100, return_dense=True)
     _, t2v_gt = get_gt(ctx["video_metas"], query_metas)
-    if _opt(opt, "double_branch", model.double_branch) and explore is not None:
-        cal_perf(-1 * inher, t2v_gt, test)
-        cal_perf(-1 * explore, t2v_gt, test)
-        a = torch.from_numpy(inher).to(opt.device)
-        b = torch.from_numpy(explore).to(opt.device)
-        fused = ops.fuse_scores(a, b, 0.7, 0.3).cpu().numpy()
-        r = cal_perf(-1 * fused, t2v_gt, test)
-    else:
-        r = cal_perf(-1 * inher, t2v_gt, test)
-    return r[0] + r[1] + r[2] + r[3]
+    pc = ctx["prepared"]
+    if _opt(opt, "per_branch_metrics", False) and model.double_branch:
+        qs, _, _ = _encode_all_queries(model, val_text_dataset, opt)
+        for bi in range(2):
+            sub = engine.PreparedCorpus(Nv=pc.Nv, L=pc.L, D=pc.D, T=pc.T, id_base=pc.id_base, mask_u8=pc.mask_u8,
+                                        lengths=pc.lengths, branches=[pc.branches[bi]], heads=pc.heads,
+                                        Lg=pc.Lg, mask_g=pc.mask_g, Pg=pc.Pg, prop_mask=pc.prop_mask)
+            pq = engine.prepare_queries([qs[bi]], want_bf16=precision == "bf16")
+            _, ids_b, dense_b = engine.rank(sub, pq, K=100, head=_opt(opt, "scoring", "frame"), precision=precision,
+                                            w_clip=model.clip_scale_w, w_frame=model.frame_scale_w, return_dense=True)
+            _log_perf(metrics_from_ranking(ids_b, dense_b, t2v_gt, pc.id_base))
+    m = metrics_from_ranking(top_ids, dense, t2v_gt, pc.id_base)
+    _log_perf(m)
+    return m[0] + m[1] + m[2] + m[3]

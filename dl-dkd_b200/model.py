@@ -215,14 +215,25 @@ class DLDKD(nn.Module):
     # ------------------------------------------------------------------ scoring (CUDA kernels)
     @staticmethod
     def get_sim_scores(modularied_query, context_feat, mask=None, want_rows=True):
-        """Cosine max-over-frames scores (method/model.py:307-329) on the exact fp32 kernels.
-        Returns (scores (M, N), per_frame (M, L, N) | None)."""
+        """Cosine max-over-frames scores (method/model.py:307-329) on the exact fp32-grade kernels.
+        Returns (scores (M, N), per_frame (M, L, N) | None).
+
+        want_rows=True reproduces the reference's second return value (the SIMT kernel writes the (M, L, N) tensor);
+        want_rows=False skips it and runs the tcgen05 kind::tf32 x 3 kernel (dkd_score_max_exact).
+        INFERENCE ONLY: the kernels build no autograd graph, so a call that would need gradients raises instead of
+        silently returning constants — the training step goes through DLDKD.forward (train.py)."""
+        if torch.is_grad_enabled() and (modularied_query.requires_grad or context_feat.requires_grad):
+            raise RuntimeError("DLDKD.get_sim_scores runs inference-only CUDA kernels (no autograd graph); call it under "
+                               "torch.no_grad(), or use DLDKD.forward / train.in_batch_similarity for the training step")
         q = modularied_query.contiguous().float()
         ctx = context_feat.contiguous().float()
         N, L, D = ctx.shape
         qn, _ = ops.normalize_rows(q)
         xn, _ = ops.normalize_rows(ctx)
         m8 = None if mask is None else (mask > 0).to(torch.uint8).contiguous()
+        if not want_rows and D % 32 == 0 and D <= 512 and L <= 128:
+            s, _ = ops.score_max_exact(qn, ops.pack_rows(xn.view(N, L, D)), L, m8)
+            return s, None
         s, _, rows = ops.score_max_f32(qn, xn.view(N, L, D), m8, want_rows=want_rows)
         return s, rows
 

@@ -27,3 +27,26 @@ class QuerySet(data.Dataset):
 
     def __getitem__(self, i):
         return self.feats[i], i, self.ids[i]
+
+
+class TeacherVideoSet(VideoSet):
+    """Items that also carry teacher (CLIP) frame features: (feat, teacher_feat, idx, id), the 4-field layout
+    collate_frame_val accepts (method/data_provider.py:144-148)."""
+
+    def __init__(self, feats, teacher, prefix="vid"):
+        super().__init__(feats, prefix)
+        self.teacher = teacher
+
+    def __getitem__(self, i):
+        return self.feats[i], self.teacher[i], i, self.ids[i]
+
+
+class TeacherQuerySet(QuerySet):
+    """(feat, teacher_text (1, Dt), idx, id): collate_text_val concatenates the teacher vectors (data_provider.py:159-160)."""
+
+    def __init__(self, feats, teacher, n_videos, prefix="vid"):
+        super().__init__(feats, n_videos, prefix)
+        self.teacher = teacher
+
+    def __getitem__(self, i):
+        return self.feats[i], self.teacher[i], i, self.ids[i]

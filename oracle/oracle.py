@@ -225,6 +225,82 @@ def topk_ids(scores, K):
     return order[:, :K]
 
 
+# ------------------------------------------------------------------- full-size parity checker (tests/, bench.py parity leg)
+def two_scale_corpus(frames_by_branch, mask, params_by_branch, T=32):
+    """Query-independent side of N1/N2/N4 for every branch: (proposals, key, val) lists (plain formulas above)."""
+    lengths = mask.sum(dim=1).long()
+    props, keys, vals = [], [], []
+    for f, (kw, kb, vw, vb) in zip(frames_by_branch, params_by_branch):
+        props.append(build_proposals(downsample_clips(f, lengths, T)))
+        keys.append(F.linear(f, kw, kb))
+        vals.append(F.linear(f, vw, vb))
+    return props, keys, vals
+
+
+def two_scale_eval_detail(q_by_branch, props, keys, vals, mask, bsz=50, w_clip=0.7, w_frame=0.3, tie_gap=2e-6):
+    """N3-N6 + the 0.7/0.3 fusion (method/eval.py:254) for EVERY (query, video) pair, in query batches so that the
+    (bsz, P, Nv) proposal-score tensor stays small.  Besides the fused matrix it returns what a parity check at the
+    named shapes needs: per branch the clip-scale score, the key clip and `tie` — True where the oracle's own best and
+    second-best proposal scores are closer than `tie_gap` (fp32 summation noise: either one is "the" key clip, and the
+    frame-scale term follows that choice).  Returns dict(fused (M, Nv) float32, clip [b], key_clip [b], tie (M, Nv))."""
+    M = q_by_branch[0].shape[0]
+    nb = len(q_by_branch)
+    outs = [[] for _ in range(nb)]
+    clips = [[] for _ in range(nb)]
+    kcs = [[] for _ in range(nb)]
+    ties = []
+    for lo in range(0, M, bsz):
+        tie = None
+        for bi, q in enumerate(q_by_branch):
+            qb = q[lo: lo + bsz]
+            s_clip, allp, kc = get_sim_scores(qb, props[bi], None)
+            top2 = torch.topk(allp, 2, dim=1).values
+            t = (top2[:, 0] - top2[:, 1]) <= tie_gap
+            tie = t if tie is None else (tie | t)
+            g = key_clip_guided_attention_batched(keys[bi], vals[bi], mask, props[bi], kc)
+            s_frame = frame_scale_scores(qb, g)
+            outs[bi].append(w_clip * s_clip + w_frame * s_frame)
+            clips[bi].append(s_clip)
+            kcs[bi].append(kc.to(torch.int32))
+        ties.append(tie)
+    sc = [torch.cat(o, dim=0).numpy() for o in outs]
+    fused = sc[0] if nb == 1 else fuse_branches(sc[0], sc[1])
+    return dict(fused=fused, branch=sc, clip=[torch.cat(c).numpy() for c in clips],
+                key_clip=[torch.cat(k).numpy() for k in kcs], tie=torch.cat(ties).numpy())
+
+
+def compare_ranking(fused_ref, tie, got_ids, K, swap_tol=1e-5):
+    """Ranked top-K lists of the device (got_ids (M, K) video ids) against the oracle's dense fused scores.
+    Tie pairs (see two_scale_eval_detail) are dropped from both lists (their score follows an equally valid other key
+    clip); what remains must be the same sequence up to swaps of oracle scores closer than `swap_tol` (the oracle list
+    is taken a few entries longer than K so that dropped tie pairs do not shorten the comparison).  Returns dict(queries_identical, swaps, tie_pairs_in_lists, mismatches) — mismatches must be 0."""
+    M = fused_ref.shape[0]
+    ref_ids = topk_ids(fused_ref, min(K + 8, fused_ref.shape[1]))
+    identical = swaps = ties_in = mismatches = 0
+    for m in range(M):
+        g, r = list(got_ids[m]), list(ref_ids[m][:K])
+        if g == r:
+            identical += 1
+            continue
+        a = [v for v in g if v >= 0 and not tie[m, v]]
+        b = [v for v in ref_ids[m] if not tie[m, v]]
+        ties_in += len(g) - len(a)
+        n = min(len(a), len(b))
+        for x, y in zip(a[:n], b[:n]):
+            if x != y:
+                if abs(float(fused_ref[m, x]) - float(fused_ref[m, y])) <= swap_tol:
+                    swaps += 1
+                else:
+                    mismatches += 1
+    return dict(queries=M, queries_identical=identical, swaps=swaps, tie_pairs_in_lists=ties_in, mismatches=mismatches)
+
+
+def recall_counts(ranks, ks=(1, 5, 10, 100)):
+    """Integer R@K numerators (#queries whose best GT ranks within K): what 'R@K identical' compares."""
+    r = np.asarray(ranks)
+    return [int(np.count_nonzero(r <= k)) for k in ks]
+
+
 # ------------------------------------------------------------------- CPU baseline (bench.py only)
 def key_clip_guided_attention_batched(key, val, mask, proposals, key_clip):
     """Vectorised (bmm) form of key_clip_guided_attention for the timed CPU baseline: same math,

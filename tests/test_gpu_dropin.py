@@ -8,7 +8,7 @@ import torch
 
 from oracle import oracle as O
 from oracle import ref_shim
-from oracle.datasets import QuerySet, VideoSet
+from oracle.datasets import QuerySet, TeacherQuerySet, TeacherVideoSet, VideoSet
 from tests import synth
 from tests.test_oracle_golden import _load, _tiny_model
 
@@ -197,3 +197,64 @@ def test_streamed_rank_equals_resident_rank(ops):
     assert torch.equal(i_st, i_all) and torch.equal(s_st, s_all)
     with pytest.raises(ValueError):
         engine.rank_streamed(iter(()), pqs, params)
+
+
+@pytest.mark.parametrize("scoring", ["frame", "two_scale"])
+def test_eval_epoch_hot_path_equals_reference_flow(ops, dkd, scoring):
+    """eval_epoch(opt.precision='bf16') — engine.rank on the device, no dense device->host copy — returns the same
+    R@1+R@5+R@10+R@100 as the reference flow (opt.precision='exact': dense matrices, eval_q2m), and rank_queries'
+    ranked lists agree with the ranking of the dense exact scores."""
+    from dkd_b200 import eval as E
+    g, m, vset, qset, opt = _tiny_setup(dkd)
+    opt.scoring = scoring
+    opt.precision = "exact"
+    rsum_ref = E.eval_epoch(m, vset, qset, opt)
+    ctx = E.compute_context_info(m, vset, opt)
+    inher, explore, _, metas = E.compute_query2ctx_info(m, qset, opt, ctx)
+    fused = O.fuse_branches(inher, explore)
+    _, t2v = E.get_gt(ctx["video_metas"], metas)
+    ref_metrics = E.eval_q2m(-1 * fused, t2v)
+    ref_map = E.t2v_map(-1 * fused, t2v)
+    opt.precision = "bf16"
+    rsum = E.eval_epoch(m, vset, qset, opt)
+    assert np.isclose(rsum, rsum_ref)
+    ctx = E.compute_context_info(m, vset, opt)
+    s, ids, metas2, dense = E.rank_queries(m, qset, opt, ctx, K=100, return_dense=True)
+    assert metas2 == metas and ids.shape[0] == len(qset) and dense.shape == fused.shape
+    Nv = len(vset)
+    assert np.array_equal(ids.cpu().numpy()[:, :Nv], O.topk_ids(fused, Nv))            # corpus smaller than K
+    assert np.abs(s.cpu().numpy()[:, :Nv] - np.take_along_axis(fused, O.topk_ids(fused, Nv), 1)).max() <= 5e-6
+    got = E.metrics_from_ranking(ids, dense, t2v)
+    assert np.allclose(got[:6], ref_metrics) and np.isclose(got[6], ref_map)
+    if scoring == "frame":      # the reference's own numbers for this fixture
+        assert np.isclose(rsum, g["metrics_fused"][:4].sum())
+
+
+def test_get_sim_scores_fast_route_and_grad_guard(ops, dkd):
+    from dkd_b200.model import DLDKD
+    g = _load("ref_sim_scores.npz")
+    q, ctx, mask = (torch.from_numpy(g[k]).cuda() for k in ("q", "ctx", "mask"))
+    s, rows = DLDKD.get_sim_scores(q, ctx, mask, want_rows=False)          # tcgen05 kind::tf32 x 3 route
+    assert rows is None and np.abs(s.cpu().numpy() - g["scores"]).max() <= 2e-6
+    with pytest.raises(RuntimeError, match="inference-only"):
+        DLDKD.get_sim_scores(q.clone().requires_grad_(True), ctx, mask)
+    with torch.no_grad():
+        DLDKD.get_sim_scores(q.clone().requires_grad_(True), ctx, mask)
+
+
+def test_teacher_items_are_scored(ops, dkd):
+    """Datasets whose items carry teacher (CLIP) features: the 4-field item layout of the reference's collate
+    functions; teacher scores = get_sim_scores on the raw teacher features (method/eval.py:198-202)."""
+    from dkd_b200 import eval as E
+    g, m, vset, qset, opt = _tiny_setup(dkd)
+    gen = torch.Generator().manual_seed(3)
+    Dt = 32
+    tv = [torch.randn(len(f), Dt, generator=gen) for f in vset.feats]
+    tq = [torch.randn(1, Dt, generator=gen) for _ in qset.feats]
+    ctx = E.compute_context_info(m, TeacherVideoSet(vset.feats, tv), opt)
+    assert ctx["teacher_frame_feat"].shape[:2] == ctx["video_mask"].shape and ctx["teacher_frame_feat"].shape[2] == Dt
+    inher, explore, teacher, metas = E.compute_query2ctx_info(m, TeacherQuerySet(qset.feats, tq, len(vset)), opt, ctx)
+    assert np.abs(inher - g["inher_scores"]).max() <= 5e-6
+    order = [qset.ids.index(x) for x in metas]
+    ref, _, _ = O.get_sim_scores(torch.cat(tq)[order], ctx["teacher_frame_feat"].cpu(), ctx["video_mask"].cpu())
+    assert teacher.shape == inher.shape and np.abs(teacher - ref.numpy()).max() <= 2e-6

@@ -71,3 +71,23 @@ def test_argument_errors_raise(ops, dkd):
         ops.topk(torch.randn(3, 10, device="cuda"), 1000)      # K > 256
     with pytest.raises(_lib.DkdError):
         ops.score_max_f32(x, torch.randn(2, 200, 48, device="cuda"))   # R > 128
+
+
+@pytest.mark.parametrize("head,L,T", [("frame", 100, 32), ("frame", 37, 32), ("two_scale", 100, 16), ("two_scale", 50, 12)])
+def test_gemm_rows_not_a_multiple_of_16(ops, head, L, T):
+    """Corpora whose rows per video are not a multiple of 16 (longest video of 100 frames; map_size 16 -> 136
+    proposals): the tcgen05 path pads every video with masked rows, and still returns the exact path's top-K."""
+    from dkd_b200 import engine
+    D, Nv, M, K = 128, 150, 70, 100
+    frames, mask, _ = synth.encoded_corpus(Nv, L, D, seed=11, min_len=max(T, 20) if head == "two_scale" else 3)
+    fr = [frames.cuda(), (frames.flip(0) * mask[:, :, None]).contiguous().cuda()]
+    pc = engine.prepare_corpus(fr, mask.cuda(), _params(D, 12), T=T, heads=(head,))
+    assert pc.Lg % 16 == 0 and pc.Pg % 16 == 0
+    pq = engine.prepare_queries([synth.encoded_queries(M, D, seed=13).cuda(), synth.encoded_queries(M, D, seed=14).cuda()])
+    s_ex, i_ex = engine.rank(pc, pq, K=K, head=head, precision="exact")
+    s_bf, i_bf = engine.rank(pc, pq, K=K, head=head, precision="bf16", Kc=128)
+    assert torch.equal(i_bf, i_ex) and torch.equal(s_bf, s_ex)
+    if head == "frame":
+        (sa, aa), _ = engine.score_frame_head(pc, pq, "bf16")
+        (se, ae), _ = engine.score_frame_head(pc, pq, "exact")
+        assert float((sa - se).abs().max()) <= 1e-3 and int(aa.max()) < L

@@ -325,8 +325,14 @@ def test_two_scale_branch_exact_path(ops):
     tf, tb = ops.frame_attn_table(key, val, clips, lc)
     fused, fr = ops.frame_fuse(qn, tf, s_clip, k_clip, 0.7, 0.3, 1.0, want_frame=True)
     assert (s_clip.cpu() - ref["clip"]).abs().max() <= FP32_TOL
+    # the key clip is bit-exact except where the oracle's own best and second-best proposal scores are closer than
+    # fp32 summation noise (documented ties, listed): there either proposal is "the" key clip
+    allp = O.clip_scale_scores(q, ref["proposals"])[1]                       # (M, P, Nv)
+    top2 = torch.topk(allp, 2, dim=1).values
+    tie = (top2[:, 0] - top2[:, 1]) <= 2e-6
     same = k_clip.cpu().long() == ref["key_clip"]
-    assert same.float().mean() > 0.999
+    assert bool((same | tie).all()), f"key clip differs outside ties at {(~(same | tie)).nonzero().tolist()[:5]}"
+    assert int(tie.sum()) <= 3, f"{int(tie.sum())} fp32 key-clip ties among {M * Nv} pairs: {tie.nonzero().tolist()[:5]}"
     assert (fr.cpu()[same] - ref["frame"][same]).abs().max() <= 5e-6
     assert (fused.cpu()[same] - ref["branch"][same]).abs().max() <= 5e-6
 

@@ -1,0 +1,110 @@
+// Micro-benchmark of the TWO-PHASE window scan (round 2): 4 warps per block (one per scheduler), one block per SM,
+// every thread scans `iters` rows.  Compared with the round-1 scan (8 running (value, index) maxima: 3 ALU-pipe
+// instructions per window) on the same inputs; results must be bit-identical (value AND first argmax).
+//
+//   phase 1  value only: run[s] += d[s+w-1]; v = run[s] * scale[w][s]; row maximum m_w by 3-input max; the best row
+//            (first w attaining the global maximum) is tracked once per ROW (32 compare/selects instead of 528)
+//   phase 2  the start s inside the best row: a sliding (inexact) window sum filters the candidates
+//            (|a * scale - best| <= tol), each candidate is recomputed with the sequential sum of phase 1 and compared
+//            for equality; the first hit is the first argmax
+//   variants: 0 = round-1 scan, 1 = two-phase scalar, 2 = two-phase with packed add.f32x2 / mul.f32x2
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scan2_micro scan2_micro.cu && ./scan2_micro
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../dl-dkd_b200/csrc/dkd_scan.cuh"
+
+using namespace dkd;
+
+template <int kVariant, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) scan_kernel(const float* __restrict__ dots, const float* __restrict__ scale,
+                                                             int iters, float* __restrict__ out_v, int* __restrict__ out_i,
+                                                             long long* cycles) {
+  __shared__ __align__(16) float sc[32 * 32];
+  __shared__ float sd[32][kWarps * 32 + 1];
+  extern __shared__ float sdyn[];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sc[i] = scale[i];
+  for (int i = 0; i < 32; ++i) sd[i][threadIdx.x] = dots[(blockIdx.x * blockDim.x + threadIdx.x) * 32 + i];
+  __syncthreads();
+  float accv = 0.f; int acci = 0;
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    asm volatile("" ::: "memory");
+    float d[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = sd[i][threadIdx.x] + (float)it * 1e-3f;
+    float bv; int bi;
+    if (kVariant == 0) window_scan_v1<true>(d, sc, 32, bv, bi);
+    else window_scan_v2<kVariant == 2>(d, sc, sdyn + threadIdx.x, kWarps * 32, bv, bi);
+    if (iters == 1) { out_v[blockIdx.x * blockDim.x + threadIdx.x] = bv; out_i[blockIdx.x * blockDim.x + threadIdx.x] = bi; }
+    accv += bv; acci += bi;
+  }
+  const long long t1 = clock64();
+  if (iters != 1) { out_v[blockIdx.x * blockDim.x + threadIdx.x] = accv; out_i[blockIdx.x * blockDim.x + threadIdx.x] = acci; }
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int kVariant, int kWarps>
+void run(const char* name, const float* dots, const float* scale, float* ov, int* oi, long long* cyc, int iters,
+         float* hv = nullptr, int* hi = nullptr) {
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaFuncSetAttribute(scan_kernel<kVariant, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kWarps * 32 * 4);
+    scan_kernel<kVariant, kWarps><<<148, kWarps * 32, 32 * kWarps * 32 * 4>>>(dots, scale, iters, ov, oi, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  }
+  long long h[148];
+  cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+  if (iters > 1) printf("%-40s %d warps/SM: %7.0f cycles per warp-scan\n", name, kWarps, avg / iters);
+  if (hv) { cudaMemcpy(hv, ov, 148 * kWarps * 32 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hi, oi, 148 * kWarps * 32 * 4, cudaMemcpyDeviceToHost); }
+}
+
+int main() {
+  const int rows = 148 * 8 * 32;
+  const int n = rows * 32;
+  float *dots, *scale, *ov; int* oi; long long* cyc;
+  cudaMalloc(&dots, n * 4); cudaMalloc(&scale, 4096); cudaMalloc(&ov, rows * 4); cudaMalloc(&oi, rows * 4);
+  cudaMalloc(&cyc, 148 * 8);
+  float* h = new float[n];
+  // three data regimes in one array: smooth positive dots (typical: all clips correlate with the query), random
+  // signs, and rows with many EXACT ties (quantised dots, constant scale) to exercise the first-argmax rule
+  for (int r = 0; r < rows; ++r)
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t x = (uint32_t)(r * 32 + i) * 2654435761u;
+      const float u = (float)((x >> 8) & 0xffff) / 65536.f;
+      float v;
+      if (r % 3 == 0) v = 0.3f + 0.05f * u;
+      else if (r % 3 == 1) v = u - 0.5f;
+      else v = (float)((x >> 12) & 3) * 0.25f;
+      h[r * 32 + i] = v;
+    }
+  cudaMemcpy(dots, h, n * 4, cudaMemcpyHostToDevice);
+  float hs[1024];
+  for (int i = 0; i < 1024; ++i) {
+    const int w = 1 + (i >> 5), s = i & 31;
+    hs[i] = (1.0f / w) * (1.0f + 0.01f * (float)((s * 7 + w * 3) % 5));     // 1 / (w * ||mean||) with a little structure
+  }
+  cudaMemcpy(scale, hs, 4096, cudaMemcpyHostToDevice);
+  float *v0 = new float[rows], *v1 = new float[rows]; int *i0 = new int[rows], *i1 = new int[rows];
+  // correctness: one scan per row, compare (value, index) bit for bit
+  run<0, 4>("v1", dots, scale, ov, oi, cyc, 1, v0, i0);
+  for (int variant = 1; variant <= 2; ++variant) {
+    if (variant == 1) run<1, 4>("v2 scalar", dots, scale, ov, oi, cyc, 1, v1, i1);
+    else run<2, 4>("v2 f32x2", dots, scale, ov, oi, cyc, 1, v1, i1);
+    int bad = 0;
+    for (int r = 0; r < 148 * 128; ++r)
+      if (v0[r] != v1[r] || i0[r] != i1[r]) { if (bad < 5) printf("  row %d: v1 (%g, %d) v2 (%g, %d)\n", r, v0[r], i0[r], v1[r], i1[r]); ++bad; }
+    printf("two-phase scan variant %d vs round-1 scan: %d of %d rows differ\n", variant, bad, 148 * 128);
+  }
+  run<0, 4>("0 round-1 scan", dots, scale, ov, oi, cyc, 200);
+  run<1, 4>("1 two-phase, scalar", dots, scale, ov, oi, cyc, 200);
+  run<2, 4>("2 two-phase, f32x2", dots, scale, ov, oi, cyc, 200);
+  run<0, 8>("0 round-1 scan", dots, scale, ov, oi, cyc, 200);
+  run<1, 8>("1 two-phase, scalar", dots, scale, ov, oi, cyc, 200);
+  run<2, 8>("2 two-phase, f32x2", dots, scale, ov, oi, cyc, 200);
+  return 0;
+}

@@ -99,7 +99,7 @@ def model_config(shape):
     return cfg, options()
 
 
-def synth_encoded(shape, device, shard_seed, dkd_model_cls):
+def synth_encoded(shape, device, shard_seed, dkd_model_cls, want_queries=True):
     """Synthetic raw features of the named shapes -> random-init DL-DKD++ encoders (PyTorch) -> encoded
     frames per branch + mask, encoded query vectors per branch.  Setup only (untimed)."""
     cfg, opt = model_config(shape)
@@ -117,6 +117,8 @@ def synth_encoded(shape, device, shard_seed, dkd_model_cls):
             a, b = model.encode_context(x, mask[lo: lo + n])
             inher.append(a)
             explore.append(b)
+        if not want_queries:
+            return model, [torch.cat(inher), torch.cat(explore)], mask, None
         gq = torch.Generator(device=device).manual_seed(5_000_000)  # queries identical on every rank
         qlen = torch.randint(5, Lq + 1, (Nq,), device=device, generator=gq)
         qi, qe = [], []
@@ -209,6 +211,66 @@ class CpuBaseline:
                 return O.two_scale_eval_detail(qs, self.props, self.keys, self.vals, self.mask, bsz=50)
             fused, _ = O.cpu_eval_frame_head(qs, self.frames, self.mask, bsz=50, K=K_TOP)
             return dict(fused=fused, tie=np.zeros_like(fused, dtype=bool))
+
+
+class ReferenceBaseline:
+    """The UNMODIFIED reference (baseline/_ref, staged by oracle/install_ref.py; imported through oracle/ref_shim.py)
+    timed on the host cores for the head it ships: compute_query2ctx_info (method/eval.py:177-219: encode_query +
+    get_sim_scores x 2 branches per batch of 50 + the dense D2H-style concatenation) -> 0.7/0.3 fusion (:254) ->
+    eval_q2m (:59-94), on `sample_queries` raw queries x the full TVR-shaped corpus.  Setup (random-init reference
+    model, synthetic raw features, the reference's own compute_context_info) is not timed."""
+
+    def __init__(self, shape, max_queries, threads=None):
+        staged = os.path.join(ROOT, "baseline", "_ref")
+        if os.path.isdir(os.path.join(staged, "method")):
+            os.environ["DKD_REFERENCE_ROOT"] = staged          # the staged copy, here and on the GPU box
+        from oracle import ref_shim
+        from oracle.datasets import QuerySet, VideoSet
+        if os.environ.get("DKD_REFERENCE_ROOT"):
+            ref_shim.REF_ROOT = os.environ["DKD_REFERENCE_ROOT"]
+        if not ref_shim.available():
+            raise RuntimeError("the reference is not staged: run `python oracle/install_ref.py` where /root/reference exists")
+        self.rm, self.re, _ = ref_shim.load()
+        self.shape, self.threads = shape, threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        cfg = ref_shim.model_config(shape["Dv"], shape["Dq"], hidden=shape["H"], max_ctx_l=shape["L"], max_desc_l=shape["Lq"])
+        self.opt = ref_shim.options()
+        torch.manual_seed(0)
+        self.model = self.rm.DLDKD(cfg, self.opt).eval()
+        g = torch.Generator().manual_seed(1000)
+        Nv, L, Dv, Lq, Dq = (shape[k] for k in ("Nv", "L", "Dv", "Lq", "Dq"))
+        vids = []
+        for _ in range(Nv):
+            x = torch.randn(L, Dv, generator=g)
+            vids.append(x / (x.norm(dim=-1, keepdim=True) + 1e-5))
+        gq = torch.Generator().manual_seed(5_000_000)
+        qlen = torch.randint(5, Lq + 1, (max_queries,), generator=gq)
+        qs = []
+        for n in range(max_queries):
+            x = torch.randn(int(qlen[n]), Dq, generator=gq)
+            qs.append(x / (x.norm(dim=-1, keepdim=True) + 1e-5))
+        self.qset_cls, self.qs, self.Nv = QuerySet, qs, Nv
+        with torch.no_grad():
+            self.ctx = self.re.compute_context_info(self.model, VideoSet(vids), self.opt)
+        self.root = ref_shim.REF_ROOT
+
+    def run(self, sample_queries):
+        qset = self.qset_cls(self.qs[:sample_queries], self.Nv)
+        t2v = {q: [q % self.Nv] for q in range(sample_queries)}
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            inher, explore, _, metas = self.re.compute_query2ctx_info(self.model, qset, self.opt, self.ctx)
+            fused = 0.7 * inher + 0.3 * explore
+            order = {m: i for i, m in enumerate(metas)}
+            gts = {order[qset.ids[q]]: t2v[q] for q in range(sample_queries)}
+            metrics = self.re.eval_q2m(-1 * fused, gts)
+            dt = time.perf_counter() - t0
+        pairs = sample_queries * self.Nv
+        return {"value": pairs / dt, "unit": "pairs/s", "cores": self.threads, "kind": "reference",
+                "sample": f"{sample_queries} raw queries x {self.Nv} videos: unmodified reference compute_query2ctx_info + "
+                          f"fusion + eval_q2m ({self.root}, torch {torch.__version__} CPU, {dt:.1f} s; R@1/5/10/100 = "
+                          f"{[round(float(x), 2) for x in metrics[:4]]})",
+                "seconds": dt}
 
 
 def run_cpu_baseline(shape, workload, sample_queries, threads=None):
@@ -344,6 +406,9 @@ def main():
     ap.add_argument("--query-batch", type=int, default=16384, help="c4_stream: queries per scoring call")
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-leg", action="store_true", help="skip timing the unmodified reference's frame head")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (fixed 17,432-video corpus)")
+    ap.add_argument("--strong-shards", type=int, default=8, help="strong scaling: corpus = this many 2,179-video shards")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
     ap.add_argument("--operand", default="bf16", choices=["bf16", "fp16", "shortcut"],
                     help="approximate pass: bf16 GEMM operands (north_star, default); IEEE-half operands (reported "
@@ -385,8 +450,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        nq = args.cpu_sample_queries or (150 if head == "two_scale" else 400)
-        cpu = CpuBaseline(cpu_shape, args.workload, nq)
+        nq = args.cpu_sample_queries or (1000 if head == "two_scale" else 4000)
+        # the head the reference ships runs the UNMODIFIED reference (kind "reference"); the two-scale head does not
+        # exist in the reference (SURVEY section 8 a-NS), so that workload times the oracle port of its eval loop
+        use_ref = args.workload == "tvr_frame"
+        cpu = ReferenceBaseline(cpu_shape, nq) if use_ref else CpuBaseline(cpu_shape, args.workload, nq)
         first = cpu.run(50)                                     # untimed: also sizes the sample
         for _ in range(max(args.warmup - 1, 0)):
             cpu.run(50)
@@ -403,7 +471,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg_common,
-                "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": last["cores"], "kind": "port",
+                "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": last["cores"], "kind": last["kind"],
                                  "sample": last["sample"]},
                 "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -428,6 +496,7 @@ def main():
     _lib.load()
 
     Nq, Nv = shape["Nq"], shape["Nv"]
+    cert_mode = ["deferred"]     # how engine.rank's candidate certificate is read: see step() below
     if stream:
         # the shard stays resident as encoded clips; operands are rebuilt chunk by chunk INSIDE the step
         frames, mask, qs, attn = synth_c4(shape, dev, rank)
@@ -459,9 +528,12 @@ def main():
         del frames
         qs = [q.contiguous() for q in qs]
 
-        def step(q_dev, precision=args.operand):
+        def step(q_dev, precision=args.operand, corpus=None):
+            # no host synchronisation inside: the candidate certificate of every call is queued on the device and
+            # resolved by engine.finish() before the lists are consumed (after the timed loop / one step later in e2e)
             pq = engine.prepare_queries(q_dev)
-            s, i = engine.rank(pc, pq, K=K_TOP, head=head, precision=precision, rescore=True, Kc=args.candidates)
+            s, i = engine.rank(corpus or pc, pq, K=K_TOP, head=head, precision=precision, rescore=True, Kc=args.candidates,
+                               certify=cert_mode[0])
             if world > 1:
                 s, i = engine.merge_shards(s, i)
             return s, i
@@ -491,6 +563,17 @@ def main():
         top_s, top_i = step(qs)
     ev[1].record()
     barrier()
+    # deferred certificates of the timed steps: a fallback (never observed at these shapes) would have been applied
+    # AFTER the timed region, so in that case the steps are timed again with the certificate read back inside each step
+    if engine.finish() and not stream:
+        cert_mode[0] = True
+        _lib.set_timed({gemm_entry})
+        barrier()
+        ev[0].record()
+        for _ in range(args.steps):
+            top_s, top_i = step(qs)
+        ev[1].record()
+        barrier()
     clocks = sampler.result()
     ms_total = ev[0].elapsed_time(ev[1])
     gemm_ms = _lib.timed_results().get(gemm_entry, [])
@@ -535,6 +618,9 @@ def main():
             for t in qd:
                 t.record_stream(main)
             s, ids = step(qd)
+            if engine.finish(keep_last=1):         # step i - 1's certificate: already on the host, no stall
+                cert_mode[0] = True                # a fallback patched lists that were already copied out: from here
+                                                   # on the certificate is read back inside the step (and e2e re-timed)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_stream):
@@ -544,6 +630,8 @@ def main():
             s.record_stream(copy_stream)
             ids.record_stream(copy_stream)
         main.wait_stream(copy_stream)          # the last result has reached host memory
+        if engine.finish():
+            cert_mode[0] = True
 
     run_e2e(1 if stream else 2)
     barrier()
@@ -553,6 +641,11 @@ def main():
     run_e2e(e2e_steps)
     ev2[1].record()
     barrier()
+    if cert_mode[0] is True and not stream:      # see run_e2e: time it again with the in-step certificate
+        ev2[0].record()
+        run_e2e(e2e_steps)
+        ev2[1].record()
+        barrier()
     e2e_ms = ev2[0].elapsed_time(ev2[1]) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
@@ -604,6 +697,51 @@ def main():
                                          "(tcgen05 kind::tf32 x 3) + window scan, fp16 frame gather, exact frame "
                                          "rescoring of the candidates; no dense GEMM, no ambiguity pass"}}
 
+    # ---- strong scaling: ONE fixed corpus of strong_shards x 2,179 videos (the concatenation of the weak-scaling
+    # shards 0..7: 17,432 videos, 62 GB of operands on one GPU), split in contiguous blocks over the N ranks; same
+    # queries, same step, same merge.  value = Nq x 17,432 / max-over-ranks time: it can fall short of N x the 1-GPU
+    # number (merge, tail effects, smaller per-rank GEMMs), unlike the weak-scaling headline.
+    strong = None
+    if not stream and not args.no_strong and head == "two_scale":
+        G = args.strong_shards
+        tot = G * Nv
+        lo, hi = engine.shard_range(tot, rank, world)
+        fr_s, mk_s = [[], []], []
+        for g in range(lo // Nv, (hi - 1) // Nv + 1):
+            _, f_g, m_g, _ = synth_encoded(shape, dev, g, DLDKD, want_queries=False)
+            a, b = max(lo, g * Nv) - g * Nv, min(hi, (g + 1) * Nv) - g * Nv
+            fr_s[0].append(f_g[0][a:b])
+            fr_s[1].append(f_g[1][a:b])
+            mk_s.append(m_g[a:b])
+        pc_s = engine.prepare_corpus([torch.cat(x) for x in fr_s], torch.cat(mk_s),
+                                     [tuple(t.detach() for t in p) for p in model.attention_params()], T=shape["T"],
+                                     heads=(head,), precisions=("exact", args.operand), id_base=lo)
+        del fr_s, mk_s
+        for _ in range(2):
+            step(qs, corpus=pc_s)
+        barrier()
+        ssteps = max(3, args.steps // 4)
+        ev4 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev4[0].record()
+        for _ in range(ssteps):
+            st_s, st_i = step(qs, corpus=pc_s)
+        ev4[1].record()
+        barrier()
+        s_ms = ev4[0].elapsed_time(ev4[1]) / ssteps
+        if world > 1:
+            t = torch.tensor([s_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ms = float(t.item())
+        # cross-check (cheap, integer): the merged lists are sorted, hold valid unique global ids
+        ok = bool((st_s[:, :-1] >= st_s[:, 1:]).all()) and int(st_i.min()) >= 0 and int(st_i.max()) < tot
+        strong = {"scaling": "strong", "corpus_videos": tot, "videos_per_gpu": hi - lo, "ms_per_step": s_ms,
+                  "value": Nq * tot / (s_ms * 1e-3), "unit": "pairs/s", "steps": ssteps, "lists_valid": ok,
+                  "checksum_ids": int(st_i.long().sum().item()),
+                  "what": "fixed corpus = weak-scaling shards 0..%d concatenated, contiguous blocks per rank; "
+                          "checksum_ids must be the same at every N" % (G - 1)}
+        del pc_s
+        torch.cuda.empty_cache()
+
     if rank == 0:
         pk = peaks()
         P = ops.num_proposals(shape["T"])
@@ -637,7 +775,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
-                "parity": parity, "variants": variants,
+                "parity": parity, "variants": variants, "strong": strong,
                 "certify": {"eps": engine.CERT_EPS, "checked_queries": engine.STATS["certify_checked_queries"],
                             "fallback_queries": engine.STATS["certify_fallback_queries"],
                             "note": "queries whose exact 100th score is within eps of the last candidate's approximate "
@@ -658,6 +796,20 @@ def main():
             cpu = CpuBaseline(cpu_shape, args.workload, nq, tensors=tensors)
             cpu.run(50)                                                   # warm the CPU kernels / allocator, untimed
             line["cpu_baseline"] = cpu.run(nq)
+            if not stream and not args.no_reference_leg:
+                # beside it: the UNMODIFIED reference (baseline/_ref) on the head it ships, same corpus shape — for
+                # the tvr_frame workload this IS the cpu_baseline (kind "reference")
+                try:
+                    nr = min(Nq, 600)
+                    refb = ReferenceBaseline(shape, nr)
+                    refb.run(50)
+                    rline = refb.run(nr)
+                    if args.workload == "tvr_frame":
+                        line["cpu_baseline_port"], line["cpu_baseline"] = line["cpu_baseline"], rline
+                    else:
+                        line["cpu_reference_frame_head"] = rline
+                except Exception as e:                                     # noqa: BLE001 - reported, not fatal
+                    line["cpu_reference_frame_head"] = {"unavailable": f"{type(e).__name__}: {e}"}
             nd = min(nq, 150)
             qd = [q[:nd].contiguous() for q in qs]
             if stream:   # the oracle's corpus slice, ranked by the same engine entry as the streamed chunks

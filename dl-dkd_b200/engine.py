@@ -276,11 +276,12 @@ class PendingCertificate:
 PENDING: List[PendingCertificate] = []
 
 
-def finish():
-    """Resolve every deferred certificate (see rank(certify="deferred")).  Returns the number of queries that had to
-    be re-ranked by the exact path."""
+def finish(keep_last=0):
+    """Resolve the deferred certificates (see rank(certify="deferred")), oldest first, all but the `keep_last` most
+    recent ones (a pipelined consumer checks call i - 1 while call i is running: that wait never stalls).  Returns the
+    number of queries that had to be re-ranked by the exact path."""
     n = 0
-    while PENDING:
+    while len(PENDING) > keep_last:
         n += PENDING.pop(0).resolve()
     return n
 
@@ -399,35 +400,36 @@ def merge_shards(local_scores, local_ids, group=None, merge_fn=None, exchange="q
         return (ms, mi) if gather else (ms, mi, (0, M))
     if exchange != "query_block":
         raise ValueError("exchange must be 'query_block' or 'all_gather'")
+    # No packing / padding / reshaping kernels: the (M, K) lists are sent as they are with ROW splits (rank g receives
+    # rows [g*Mb, (g+1)*Mb) of every rank), the merge kernel writes this rank's block into a fixed-size (Mb, K)
+    # buffer, and the all-gather of those buffers IS the (world*Mb, K) result in query order — [:M] is a view.
     rank_ = dist.get_rank(group)
     Mb = (M + world - 1) // world
-    # (score bits, id) packed per destination: send[g] = my lists for query block g, padded with (-inf, -1)
-    send = torch.empty((world, 2, Mb, K), dtype=torch.int32, device=dev)
-    pad = world * Mb - M
-    sc = local_scores.contiguous().view(torch.int32)
-    if pad:
-        neg_inf = torch.full((pad, K), float("-inf"), dtype=torch.float32, device=dev).view(torch.int32)
-        sc = torch.cat([sc, neg_inf])
-        ids = torch.cat([local_ids, torch.full((pad, K), -1, dtype=torch.int32, device=dev)])
-    else:
-        ids = local_ids
-    send[:, 0] = sc.view(world, Mb, K)
-    send[:, 1] = ids.view(world, Mb, K)
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
-    bs, bi = merge_fn(recv[:, 0].contiguous().view(torch.float32), recv[:, 1].contiguous())      # (Mb, K): my block
     q_lo, q_hi = min(rank_ * Mb, M), min((rank_ + 1) * Mb, M)
-    if not gather:
-        return bs[: q_hi - q_lo], bi[: q_hi - q_lo], (q_lo, q_hi)
-    mine = torch.stack([bs.contiguous().view(torch.int32), bi])                                     # (2, Mb, K)
-    full = torch.empty((world, 2, Mb, K), dtype=torch.int32, device=dev)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(full, mine, group=group)
+    mine = q_hi - q_lo
+    in_split = [min((g + 1) * Mb, M) - min(g * Mb, M) for g in range(world)]
+    rs = torch.empty((world, mine, K), dtype=torch.float32, device=dev)
+    ri = torch.empty((world, mine, K), dtype=torch.int32, device=dev)
+    dist.all_to_all_single(rs.view(world * mine, K), local_scores.contiguous(), [mine] * world, in_split, group=group)
+    dist.all_to_all_single(ri.view(world * mine, K), local_ids.contiguous(), [mine] * world, in_split, group=group)
+    if mine:
+        bs, bi = merge_fn(rs, ri)                                                       # (mine, K): my query block
     else:
-        dist.all_gather(list(full.unbind(0)), mine, group=group)
-    ms = full[:, 0].reshape(world * Mb, K)[:M].contiguous().view(torch.float32)
-    mi = full[:, 1].reshape(world * Mb, K)[:M].contiguous()
-    return ms, mi
+        bs, bi = rs.new_empty((0, K)), ri.new_empty((0, K))
+    if not gather:
+        return bs, bi, (q_lo, q_hi)
+    if mine != Mb:       # only the last block(s) can be short: pad to the common size (-inf, -1), sliced away below
+        bs = torch.cat([bs, bs.new_full((Mb - mine, K), float("-inf"))])
+        bi = torch.cat([bi, bi.new_full((Mb - mine, K), -1)])
+    fs = torch.empty((world * Mb, K), dtype=torch.float32, device=dev)
+    fi = torch.empty((world * Mb, K), dtype=torch.int32, device=dev)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(fs, bs.contiguous(), group=group)
+        dist.all_gather_into_tensor(fi, bi.contiguous(), group=group)
+    else:
+        dist.all_gather(list(fs.view(world, Mb, K).unbind(0)), bs.contiguous(), group=group)
+        dist.all_gather(list(fi.view(world, Mb, K).unbind(0)), bi.contiguous(), group=group)
+    return fs[:M], fi[:M]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -8,7 +8,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DKD_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _default_root():
+    """DKD_REFERENCE_ROOT, else the source tree (this container), else the staged byte-identical copy that travels to
+    the GPU box (baseline/_ref, oracle/install_ref.py)."""
+    env = os.environ.get("DKD_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if os.path.isdir("/root/reference/method") else _STAGED
+
+
+REF_ROOT = _default_root()
 
 
 def available() -> bool:

@@ -407,6 +407,9 @@ def main():
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-leg", action="store_true", help="skip timing the unmodified reference's frame head")
+    ap.add_argument("--no-c4", action="store_true", help="skip the reduced c4_stream sub-measurement")
+    ap.add_argument("--c4-sub-videos", type=int, default=32768)
+    ap.add_argument("--c4-sub-queries", type=int, default=16384)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (fixed 17,432-video corpus)")
     ap.add_argument("--strong-shards", type=int, default=8, help="strong scaling: corpus = this many 2,179-video shards")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e / parity / cpu legs")
@@ -742,6 +745,45 @@ def main():
         del pc_s
         torch.cuda.empty_cache()
 
+    # ---- BASELINE.json configs[3] at a driver-runnable size (the default run has no flags): the streamed engine on
+    # c4_sub_videos clip-feature videos PER GPU x c4_sub_queries queries, chunked exactly like the full config
+    # (--workload c4_stream runs the 125 k x 100 k per-GPU size), operand building inside the step, N-way merge.
+    c4 = None
+    if not stream and not args.no_c4 and head == "two_scale":
+        c4shape = dict(Nv=args.c4_sub_videos, L=32, Dv=None, Nq=args.c4_sub_queries, Lq=None, Dq=None, H=384, T=32)
+        fr4, mk4, q4, at4 = synth_c4(c4shape, dev, rank)
+
+        def c4_step(precision=args.operand):
+            pqs = engine.split_queries(q4, args.query_batch)
+            chunks = engine.iter_chunks(fr4, mk4, args.chunk_videos, id_base=rank * c4shape["Nv"])
+            s4, i4 = engine.rank_streamed(chunks, pqs, at4, K=K_TOP, T=32, precision=precision, Kc=args.candidates)
+            if world > 1:
+                s4, i4 = engine.merge_shards(s4, i4)
+            return s4, i4
+
+        c4_step()
+        barrier()
+        c4steps = 2
+        ev5 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev5[0].record()
+        for _ in range(c4steps):
+            c4_s, c4_i = c4_step()
+        ev5[1].record()
+        barrier()
+        c4_ms = ev5[0].elapsed_time(ev5[1]) / c4steps
+        if world > 1:
+            t = torch.tensor([c4_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c4_ms = float(t.item())
+        e4_s, e4_i = c4_step(precision="exact") if world == 1 else (c4_s, c4_i)
+        c4 = {"workload": "c4_stream (reduced)", "videos_per_gpu": c4shape["Nv"], "queries": c4shape["Nq"],
+              "chunk_videos": args.chunk_videos, "query_batch": args.query_batch, "ms_per_step": c4_ms, "steps": c4steps,
+              "value": c4shape["Nq"] * c4shape["Nv"] * world / (c4_ms * 1e-3), "unit": "pairs/s",
+              "top100_identical_to_exact_fp32": bool(torch.equal(e4_i, c4_i) and torch.equal(e4_s, c4_s)) if world == 1 else None,
+              "what": "rank_streamed: operands of every 8,192-video chunk rebuilt inside the step, running top-100 fold"}
+        del fr4, mk4, q4
+        torch.cuda.empty_cache()
+
     if rank == 0:
         pk = peaks()
         P = ops.num_proposals(shape["T"])
@@ -775,7 +817,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
-                "parity": parity, "variants": variants, "strong": strong,
+                "parity": parity, "variants": variants, "strong": strong, "c4_stream": c4,
                 "certify": {"eps": engine.CERT_EPS, "checked_queries": engine.STATS["certify_checked_queries"],
                             "fallback_queries": engine.STATS["certify_fallback_queries"],
                             "note": "queries whose exact 100th score is within eps of the last candidate's approximate "

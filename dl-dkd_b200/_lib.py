@@ -27,7 +27,7 @@ PROTOTYPES = {
     "dkd_score_max_exact": [_P, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _P, _P],
     "dkd_clip_planes_bytes": [_I, _I],
     "dkd_pack_clips_tf32": [_P, _I, _I, _I, _P, _P],
-    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P],
+    "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _L, _P],
     "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _F, _P],
     "dkd_score_max_f16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _F, _P],
     "dkd_build_proposals_f16": [_P, _I, _I, _I, _P, _P, _P],
@@ -44,7 +44,14 @@ PROTOTYPES = {
     "dkd_frame_fuse_csr": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _L, _P],
     "dkd_scatter_fuse": [_P, _P, _F, _F, _P, _P, _I, _L, _P, _P],
     "dkd_sort_candidates": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "dkd_weight_planes_bytes": [_I, _I],
+    "dkd_pack_weight_tf32": [_P, _I, _I, _P, _P],
+    "dkd_linear_exact": [_P, _L, _I, _P, _I, _P, _I, _P, _P, _L, _P],
+    "dkd_row_stats": [_P, _L, _I, _F, _P, _P],
+    "dkd_layernorm_rows": [_P, _L, _L, _I, _P, _P, _F, _P, _L, _P, _I, _P, _P],
+    "dkd_mha_small": [_P, _L, _I, _I, _I, _P, _I, _I, _I, _I, _F, _P, _L, _P],
     "dkd_row_inv_norms": [_P, _L, _I, _F, _P, _P],
+    "dkd_train_curve": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
     "dkd_train_sim_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "dkd_train_sim_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dkd_kl_curve_loss": [_P, _P, _P, _I, _I, _F, _P, _P, _P],
@@ -52,6 +59,7 @@ PROTOTYPES = {
     "dkd_train_losses": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _F, _F, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {"dkd_error_string": c_char_p, "dkd_clip_planes_bytes": c_int64, "dkd_row_planes_bytes": c_int64,
+             "dkd_weight_planes_bytes": c_int64,
              "dkd_train_losses_workspace_floats": c_int64}
 
 _lib = None

@@ -58,9 +58,22 @@ struct ExactParams {
   unsigned wait_ns;            // sleep between mbarrier polls of the non-critical warps (0: spin)
   // mode 2 (dense clip windows, kXGroup videos per tile): Nv = number of WORK ITEMS = video groups x tile chunks
   int Nv_real, tile_chunks, tiles_per_chunk;
+  // mode 4 (linear layer: out = act(x_hat . W^T + bias)): "videos" are 128-row tiles of the packed weight matrix,
+  // work items = (row chunk, weight tile) with the weight tile fastest (CTAs running together share the rows of x in L2)
+  const int32_t* known_key;    // mode 0, optional: dense (M, known_ld) key clips to confirm (dkd_scan.cuh window_scan_known)
+  int64_t known_ld;
+  const float2* row_ss;        // optional per-row (scale, shift): x_hat = x * scale + shift (LayerNorm prologue)
+  const float* bias;           // optional (n_cols)
+  int relu, n_cols;
 };
 constexpr int kXGroup = 4;                   // mode 2: videos sharing one staged A tile (UMMA N = 4 x 32 clips)
-constexpr bool kXPackedScan = false;         // window sums / products two at a time (add.rn.f32x2): see dkd_scan.cuh
+// Which window scan runs (dkd_scan.cuh; measured in isolation by tools/micro/scan2_micro.cu, profiles/r2_scan_micro.md):
+//   list forms (mode 0: ONE scan warp per scheduler, latency bound)  two-phase scan with packed add / mul.f32x2
+//                                                                   (5.2 k cycles per warp-scan against 7.4 k), or the
+//                                                                   known-key form when the caller passes key clips;
+//   dense form (mode 2: two scan warps per scheduler, pipe bound)    v1 (the two-phase scan gains nothing there).
+constexpr bool kXTwoPhaseList = true;
+constexpr bool kXPackedScan = true;
 
 struct __align__(8) ExactCtl {
   uint64_t a_full[kXMaxAStages], a_empty[kXMaxAStages];
@@ -133,6 +146,15 @@ __device__ __forceinline__ void item_range(const ExactParams& p, int item, int& 
   count = p.M - row0 < rows ? p.M - row0 : rows;
 }
 
+// mode 4 work item -> (weight tile, first row, number of rows): weight tile fastest
+__device__ __forceinline__ void item_range_linear(const ExactParams& p, int item, int& wtile, int& row0, int& count) {
+  wtile = item % p.Nv_real;
+  const int chunk = item / p.Nv_real;
+  row0 = chunk * p.tiles_per_chunk * kXRows;
+  const int rows = p.tiles_per_chunk * kXRows;
+  count = p.M - row0 < rows ? p.M - row0 : rows;
+}
+
 // kMode 0: clip windows (B = the video's 32 clips, resident; scan = T(T+1)/2 window cosines).
 // kMode 1: rows max (B = the video's R <= 128 rows, streamed per K block through a ring; scan = masked max).
 // kMode 2: clip windows, DENSE only.  Measurements (tools/micro/scan_micro.cu): one window scan is a
@@ -143,13 +165,16 @@ __device__ __forceinline__ void item_range(const ExactParams& p, int item, int& 
 //          form one N = 128 B operand, streamed per K block like mode 1), which cuts the staging work per pair 4 x, so
 //          one stager warp per TMEM lane quarter (warps 4-7) is enough.  Same 14 warps, same 128 registers per thread.
 //          Modes 0 / 1 keep one scan group and two stager sets (list forms: every video has its own query list).
+// kMode 4: linear layer on the same pipeline as mode 1 (fp32-grade tf32 x 3): A = rows of x (optionally normalised on
+//          the fly by a per-row scale / shift: the LayerNorm in front of the projection), B = a 128-row tile of the
+//          pre-packed weight matrix streamed per K block, epilogue = + bias, optional ReLU, fp32 store of the tile.
 template <int kMode, bool kT32, int kXRing>
 __global__ void __launch_bounds__(kXThreads, 1)
 exact_umma_kernel(const ExactParams p) {
   constexpr int kDW = kMode == 0 ? 32 : 128;                    // accumulator columns per TMEM buffer
   constexpr int kScaleBufs = kMode == 2 ? kXGroup : 2;
   constexpr int kStageSets = kMode == 2 ? 1 : 2;                // stager warps per TMEM lane quarter
-  constexpr int kScanGroups = kMode == 2 ? 2 : (kMode == 0 ? 1 : 0);
+  constexpr int kScanGroups = (kMode == 0 && kXTwoPhaseList) ? 1 : 0;   // scan scratch (two-phase / known-key scans)
   constexpr uint32_t kXACol0 = 2 * kDW;                         // first A-ring column
   constexpr int kXStages = (kXTmemCols - 2 * kDW) / 64;         // A ring stages: 7 / 4
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
@@ -203,8 +228,11 @@ exact_umma_kernel(const ExactParams p) {
     for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
       int e0, count, row_base = 0;
       if (kMode == 2) { int g_; item_range(p, n, g_, row_base, count); e0 = 0; }
+      else if (kMode == 4) { int g_; item_range_linear(p, n, g_, row_base, count); e0 = 0; }
       else video_range(p, n, e0, count);
       if (count <= 0) continue;
+      int ss_tile = -1;                                         // mode 4: tile whose row scale / shift is cached
+      float2 ss[4];
       const int nitems = ((count + kXRows - 1) / kXRows) * num_kb;
       // item j = (tile j / num_kb, K block j % num_kb) of this video
       int t_cached = -1;
@@ -245,6 +273,27 @@ exact_umma_kernel(const ExactParams p) {
           for (int c = 0; c < 2; ++c)
             v[2 * hu + c] = *reinterpret_cast<const float4*>(
                 slot + (16 * (hu >> 1) + g + 8 * (hu & 1)) * kXRowPitch + (((4 * c + t) ^ ((g & 1) << 2)) << 4));
+        if (kMode == 4) {
+          if (p.row_ss) {                                       // x_hat = x * scale + shift of the row (LayerNorm prologue)
+            const int tile_j = j / num_kb;
+            if (tile_j != ss_tile) {
+              ss_tile = tile_j;
+#pragma unroll
+              for (int hu = 0; hu < 4; ++hu) {
+                const int r = tile_j * kXRows + quarter * 32 + 16 * (hu >> 1) + g + 8 * (hu & 1);
+                ss[hu] = r < count ? __ldg(p.row_ss + row_base + r) : make_float2(0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int hu = 0; hu < 4; ++hu)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                float4& x = v[2 * hu + c];
+                x.x = fmaf(x.x, ss[hu].x, ss[hu].y); x.y = fmaf(x.y, ss[hu].x, ss[hu].y);
+                x.z = fmaf(x.z, ss[hu].x, ss[hu].y); x.w = fmaf(x.w, ss[hu].x, ss[hu].y);
+              }
+          }
+        }
         const uint32_t it = it_base + (uint32_t)j;
         const uint32_t stage = it % (uint32_t)kXStages;
         const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
@@ -321,7 +370,9 @@ exact_umma_kernel(const ExactParams p) {
           }
           continue;
         }
-        video_range(p, n, e0, count);
+        int vid = n;
+        if (kMode == 4) { int r0_; item_range_linear(p, n, vid, r0_, count); }
+        else video_range(p, n, e0, count);
         if (count <= 0) continue;
         if (kMode == 0) {
           const uint32_t bb = vi % b_bufs;
@@ -334,7 +385,7 @@ exact_umma_kernel(const ExactParams p) {
                       2 * kXBPlane, &ctl->b_full[bb]);
         } else {
           // every tile of the video streams the video's row planes again (L2 resident): one stage per K block
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)n * num_kb * b_buf_bytes;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.planes) + (size_t)vid * num_kb * b_buf_bytes;
           for (int t0 = 0; t0 < count; t0 += kXRows) {
             for (int kb = 0; kb < num_kb; ++kb, ++itb) {
               const uint32_t bs = itb % (uint32_t)kXBStages;
@@ -357,6 +408,7 @@ exact_umma_kernel(const ExactParams p) {
     for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
       int e0, count;
       if (kMode == 2) { int g_, r_; item_range(p, n, g_, r_, count); e0 = 0; }
+      else if (kMode == 4) { int g_, r_; item_range_linear(p, n, g_, r_, count); e0 = 0; }
       else video_range(p, n, e0, count);
       if (count <= 0) continue;
       uint32_t bb = 0;
@@ -455,8 +507,7 @@ exact_umma_kernel(const ExactParams p) {
           for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
           float bv0;
           int bi0;
-          if constexpr (kT32) window_scan_v2<kXPackedScan>(d, sc, sD + part * (kXScanScratch / 4) + quarter * 32 + lane, kXRows, bv0, bi0);
-          else window_scan_v1<false>(d, sc, T, bv0, bi0);
+          window_scan_v1<kT32>(d, sc, T, bv0, bi0);
           const int vid = group * kXGroup + v;
           if (r < p.M && t0 + quarter * 32 + lane < count && vid < p.Nv_real) {
             const int64_t o = (int64_t)r * p.ld_out + vid;
@@ -508,14 +559,68 @@ exact_umma_kernel(const ExactParams p) {
         for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(raw[i]);
         float bv0;
         int bi0;
-        if constexpr (kT32) window_scan_v2<kXPackedScan>(d, sc, sD + quarter * 32 + lane, kXRows, bv0, bi0);
-        else window_scan_v1<false>(d, sc, T, bv0, bi0);
         const int r = t0 + quarter * 32 + lane;
+        if constexpr (kT32 && kXTwoPhaseList) {
+          float* dcol = sD + quarter * 32 + lane;
+          if (p.known_key) {
+            // candidates whose key clip is already fixed: confirm it against the value-only maximum
+            const int qi = r < count ? (p.q_list ? p.q_list[e0 + r] : r) : 0;
+            const int key = r < count ? __ldg(p.known_key + (int64_t)qi * p.known_ld + n) : 0;
+            window_scan_known<kXPackedScan>(d, sc, dcol, kXRows, key, bv0, bi0);
+          } else {
+            window_scan_v2<kXPackedScan>(d, sc, dcol, kXRows, bv0, bi0);
+          }
+        } else {
+          window_scan_v1<kT32>(d, sc, T, bv0, bi0);
+        }
         if (r < count) {
           const int64_t o = p.out_slot ? (int64_t)p.out_slot[e0 + r]
                                        : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n);
           p.out_max[o] = bv0;
           if (p.out_arg) p.out_arg[o] = bi0;
+        }
+      }
+    }
+  } else if constexpr (kMode == 4) {
+    // ===================== epilogue of the linear layer: + bias, optional ReLU, fp32 store =====================
+    // Thread = tile row: its 128 outputs arrive as four 32-column TMEM loads and leave as 16-byte stores.
+    const int quarter = warp;
+    uint32_t tc = 0;
+    for (int n = blockIdx.x; n < p.Nv; n += gridDim.x) {
+      int wtile, row0, count;
+      item_range_linear(p, n, wtile, row0, count);
+      if (count <= 0) continue;
+      for (int t0 = 0; t0 < count; t0 += kXRows, ++tc) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(&ctl->tmem_full[buf], (tc >> 1) & 1u);
+        tc_fence_after();
+        const int r = t0 + quarter * 32 + lane;
+        const bool live = r < count;
+        float* orow = p.out_max + (int64_t)(row0 + (live ? r : 0)) * p.ld_out;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)kDW + (uint32_t)c0, raw);
+          tmem_ld_wait();
+          if (c0 == 96) {                          // the accumulator buffer is free once its last slice is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = wtile * 128 + c0 + j;
+            if (live && col < p.n_cols) {
+              float4 o = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                                     __uint_as_float(raw[j + 3]));
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(orow + col) = o;
+            }
+          }
         }
       }
     }
@@ -575,7 +680,8 @@ exact_umma_kernel(const ExactParams p) {
 // Pre-pack the rows of every video (clips, or frames) into the shared-memory image of the exact kernels' B operand:
 // planes[n][kb][plane][rpad rows x 128 B, SWIZZLE_128B], plane 0 = tf32 hi, 1 = tf32 lo, rows >= R zero, features
 // of a K block permuted like the A operand (feature 16c + 4t + 2b + e at position 16c + 8b + 2t + e).
-__global__ void pack_rows_tf32_kernel(const float* __restrict__ x, int R, int rpad, int D, float* __restrict__ planes) {
+__global__ void pack_rows_tf32_kernel(const float* __restrict__ x, int R, int rpad, int D, float* __restrict__ planes,
+                                      int64_t total_rows) {
   const int n = blockIdx.x;
   const int num_kb = D / kXKB;
   const uint32_t plane_bytes = (uint32_t)rpad * 128u;
@@ -584,7 +690,7 @@ __global__ void pack_rows_tf32_kernel(const float* __restrict__ x, int R, int rp
     const int kb = i / (rpad * 8), rem = i - kb * rpad * 8;
     const int r = rem >> 3, c8 = rem & 7;                           // float4 c8: features 4 c8 .. 4 c8 + 3
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < R) v = *reinterpret_cast<const float4*>(x + ((int64_t)n * R + r) * D + kb * kXKB + c8 * 4);
+    if (r < R && (int64_t)n * R + r < total_rows) v = *reinterpret_cast<const float4*>(x + ((int64_t)n * R + r) * D + kb * kXKB + c8 * 4);
     uint2 h0, l0, h1, l1;
     split_tf32(v.x, h0.x, l0.x); split_tf32(v.y, h0.y, l0.y); split_tf32(v.z, h1.x, l1.x); split_tf32(v.w, h1.y, l1.y);
     const int cc = c8 >> 2, tt = c8 & 3;
@@ -619,7 +725,7 @@ static int pack_rows(const float* x, int32_t Nv, int32_t R, int32_t rpad, int32_
   if (R <= 0 || R > rpad || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(planes)) & 15) return DKD_ERR_ALIGN;
   if (Nv == 0) return DKD_OK;
-  pack_rows_tf32_kernel<<<Nv, 256, 0, (cudaStream_t)stream>>>(x, R, rpad, D, planes);
+  pack_rows_tf32_kernel<<<Nv, 256, 0, (cudaStream_t)stream>>>(x, R, rpad, D, planes, (int64_t)Nv * R);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }
@@ -640,9 +746,9 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_kb = D / kXKB;
-  const int ring = D > 448 ? 2 : 3;
+  const int ring = (mode == 0 || mode == 2) && D > 448 ? 2 : 3;   // clip modes: the resident B buffer grows with D
   const int ring_warps = mode == 2 ? 4 : kXStageWarps;        // mode 2: one stager warp per TMEM lane quarter
-  const int scan_groups = mode == 2 ? 2 : (mode == 0 ? 1 : 0);
+  const int scan_groups = (mode == 0 && kXTwoPhaseList) ? 1 : 0;
   const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 16384 /* static shared, largest mode */ +
                        (size_t)ring_warps * ring * kXSlotBytes + (size_t)scan_groups * kXScanScratch;
   size_t b_total;
@@ -670,8 +776,10 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
   } else if (mode == 2) {
     if (ring == 3) rc = (T == 32) ? launch(exact_umma_kernel<2, true, 3>) : launch(exact_umma_kernel<2, false, 3>);
     else rc = (T == 32) ? launch(exact_umma_kernel<2, true, 2>) : launch(exact_umma_kernel<2, false, 2>);
+  } else if (mode == 4) {
+    rc = launch(exact_umma_kernel<4, true, 3>);
   } else {
-    rc = (ring == 3) ? launch(exact_umma_kernel<1, true, 3>) : launch(exact_umma_kernel<1, true, 2>);
+    rc = launch(exact_umma_kernel<1, true, 3>);
   }
   if (rc) return rc;
   DKD_LAUNCH_CHECK();
@@ -698,10 +806,12 @@ extern "C" int dkd_score_max_exact(const float* qn, int32_t M, const float* row_
 extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
                                   int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
                                   int64_t ld_out, const int32_t* vid_ptr, const int32_t* vid_cnt,
-                                  const int32_t* q_list, const int32_t* out_slot, void* stream) {
+                                  const int32_t* q_list, const int32_t* out_slot, const int32_t* known_key,
+                                  int64_t known_ld, void* stream) {
   if (!qn || !clip_planes || !prop_scale || !out_max || M < 0 || Nv < 0) return DKD_ERR_ARG;
   if ((vid_ptr == nullptr) != (q_list == nullptr)) return DKD_ERR_ARG;
   if ((out_slot || vid_cnt) && !vid_ptr) return DKD_ERR_ARG;
+  if (known_key && (!vid_ptr || known_ld < Nv || T != 32)) return DKD_ERR_ARG;
   if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
   if (!vid_ptr && ld_out < Nv) return DKD_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(clip_planes) | reinterpret_cast<uintptr_t>(prop_scale)) & 15)
@@ -712,6 +822,7 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
   p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
   p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
   p.vid_ptr = vid_ptr; p.vid_cnt = vid_cnt; p.q_list = q_list; p.out_slot = out_slot;
+  p.known_key = known_key; p.known_ld = known_ld;
   if (!vid_ptr && Nv >= kXGroup) {
     // dense form (mode 2): work items = groups of 4 videos x chunks of query tiles, several items per SM
     const int groups = (Nv + kXGroup - 1) / kXGroup;
@@ -728,4 +839,46 @@ extern "C" int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_
     return launch_exact(2, p, D, T, (cudaStream_t)stream);
   }
   return launch_exact(0, p, D, T, (cudaStream_t)stream);
+}
+
+// ---- linear layers of the corpus-side encoder on the same fp32-grade tensor-core pipeline ----
+extern "C" int64_t dkd_weight_planes_bytes(int32_t N, int32_t K) {
+  if (N <= 0 || K <= 0 || K % kXKB != 0) return -1;
+  return (int64_t)((N + 127) / 128) * (K / kXKB) * 2 * 128 * 128;
+}
+
+extern "C" int dkd_pack_weight_tf32(const float* w, int32_t N, int32_t K, float* planes, void* stream) {
+  if (!w || !planes || N <= 0) return DKD_ERR_ARG;
+  if (K <= 0 || K % kXKB != 0) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(planes)) & 15) return DKD_ERR_ALIGN;
+  pack_rows_tf32_kernel<<<(N + 127) / 128, 256, 0, (cudaStream_t)stream>>>(w, 128, 128, K, planes, (int64_t)N);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_linear_exact(const float* x, int64_t M, int32_t K, const float* w_planes, int32_t N,
+                                const float* bias, int32_t relu, const float* row_scale_shift, float* out,
+                                int64_t ld_out, void* stream) {
+  if (!x || !w_planes || !out || M < 0 || N <= 0) return DKD_ERR_ARG;
+  if (K <= 0 || K % kXKB != 0 || N % 4 != 0 || ld_out < N || ld_out % 4 != 0 || M > 0x7fffff00LL) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_planes) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(row_scale_shift)) & 15)
+    return DKD_ERR_ALIGN;
+  if (M == 0) return DKD_OK;
+  ExactParams p{};
+  p.q = x; p.M = (int)M; p.planes = w_planes; p.scale = nullptr;
+  p.T = 0; p.D = K; p.R = 128; p.Npad = 128; p.mask = nullptr;
+  p.out_max = out; p.out_arg = nullptr; p.ld_out = ld_out;
+  p.row_ss = reinterpret_cast<const float2*>(row_scale_shift); p.bias = bias; p.relu = relu; p.n_cols = N;
+  const int wtiles = (N + 127) / 128;
+  const int tiles = (int)((M + kXRows - 1) / kXRows);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int chunks = 1;
+  while (chunks < tiles && (int64_t)wtiles * chunks < (int64_t)sms * 6) ++chunks;
+  p.tiles_per_chunk = (tiles + chunks - 1) / chunks;
+  p.tile_chunks = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.Nv_real = wtiles;
+  p.Nv = wtiles * p.tile_chunks;
+  return launch_exact(4, p, K, 0, (cudaStream_t)stream);
 }

@@ -80,17 +80,12 @@ __device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
   return r;
 }
 
-// T = 32 only.  dcol: this thread's column of a shared-memory scratch of 32 rows (dcol[i * dstride] = d[i]); it is
-// written here and only read by the same thread, so no barrier is needed.
+// ---- two-phase scan (T = 32 only) ---------------------------------------------------------------------------------
+// phase 1: maximum VALUE over all windows and the first row (window length) attaining it.
 template <bool kPacked>
-__device__ __forceinline__ void window_scan_v2(const float (&d)[32], const float* __restrict__ sc, float* dcol, int dstride,
-                                               float& out_v, int& out_i) {
-  // |d| mass: bounds every partial window sum, hence the error of the sliding sums of phase 2
-  float mass = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) { dcol[i * dstride] = d[i]; mass += fabsf(d[i]); }
-  float best = -INFINITY;
-  int bw = 1;
+__device__ __forceinline__ void scan_phase1(const float (&d)[32], const float* __restrict__ sc, float& best, int& bw) {
+  best = -INFINITY;
+  bw = 1;
   if (!kPacked) {
     float run[32];
 #pragma unroll
@@ -149,32 +144,108 @@ __device__ __forceinline__ void window_scan_v2(const float (&d)[32], const float
       if (mw > best) { best = mw; bw = w; }
     }
   }
-  // ---- phase 2: first start of row bw whose value equals `best`
+}
+
+// exact value of window (length w, start s): the sequential sum of phase 1, read back from the thread's column of the
+// shared-memory scratch (dynamic start); all 32 loads are issued up front, the adds are predicated on i < w
+__device__ __forceinline__ float window_value(const float* dcol, int dstride, const float* __restrict__ sc, int w, int s) {
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = dcol[min(s + i, 31) * dstride];
+  float r = x[0];
+#pragma unroll
+  for (int i = 1; i < 32; ++i) r = (i < w) ? __fadd_rn(r, x[i]) : r;
+  return __fmul_rn(r, sc[(w - 1) * 32 + s]);
+}
+
+// phase 2: the first start s of row bw whose value equals `best`.  Straight-line code with static register indices:
+// a sliding (inexact) window sum flags the starts whose value can equal the maximum (bit mask), only those are
+// recomputed exactly (window_value) — normally one per thread, all threads of the warp in lock step.
+__device__ __forceinline__ int scan_phase2(const float (&d)[32], const float* __restrict__ sc, const float* dcol, int dstride,
+                                           float best, int bw, float mass) {
+  float a = d[0];
+#pragma unroll
+  for (int i = 1; i < 32; ++i) a = (i < bw) ? __fadd_rn(a, d[i]) : a;       // start 0, exact
   const float* scr = sc + (bw - 1) * 32;
   const float tol = 1.0e-5f * mass;                      // >= 93 roundings of 2^-24 * mass (sliding + sequential sums)
-  float a = dcol[0];
-  for (int i = 1; i < bw; ++i) a = __fadd_rn(a, dcol[i * dstride]);       // exact value of start 0
-  int s_found = -1;
-  const int ns = 33 - bw;
-  for (int s = 0; s < ns; ++s) {
-    const float scl = scr[s];
-    if (fabsf(__fmul_rn(a, scl) - best) <= tol * fabsf(scl)) {
-      float r = dcol[s * dstride];
-      for (int i = 1; i < bw; ++i) r = __fadd_rn(r, dcol[(s + i) * dstride]);
-      if (__fmul_rn(r, scl) == best) { s_found = s; break; }
+  uint32_t cand = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float t[8], scl[8];
+    *reinterpret_cast<float4*>(&scl[0]) = *reinterpret_cast<const float4*>(&scr[8 * c]);
+    *reinterpret_cast<float4*>(&scl[4]) = *reinterpret_cast<const float4*>(&scr[8 * c + 4]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = dcol[min(8 * c + j + bw, 31) * dstride];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int s = 8 * c + j;
+      const bool ok = (s + bw <= 32) && (fabsf(__fmul_rn(a, scl[j]) - best) <= tol * fabsf(scl[j]));
+      cand |= (ok ? 1u : 0u) << s;
+      a = __fadd_rn(__fadd_rn(a, -d[s]), t[j]);
     }
-    if (s + 1 < ns) a = __fadd_rn(__fadd_rn(a, -dcol[s * dstride]), dcol[(s + bw) * dstride]);
+  }
+  int s_found = -1;
+  while (cand) {
+    const int s = __ffs(cand) - 1;
+    cand &= cand - 1;
+    if (window_value(dcol, dstride, sc, bw, s) == best) { s_found = s; break; }
   }
   if (s_found < 0) {                                      // unreachable unless the filter bound is violated: full search
-    for (int s = 0; s < ns && s_found < 0; ++s) {
-      float r = dcol[s * dstride];
-      for (int i = 1; i < bw; ++i) r = __fadd_rn(r, dcol[(s + i) * dstride]);
-      if (__fmul_rn(r, scr[s]) == best) s_found = s;
-    }
+    for (int s = 0; s + bw <= 32 && s_found < 0; ++s)
+      if (window_value(dcol, dstride, sc, bw, s) == best) s_found = s;
     if (s_found < 0) s_found = 0;
   }
+  return s_found;
+}
+
+// dcol: this thread's column of a shared-memory scratch of 32 rows (dcol[i * dstride] = d[i]); it is written here and
+// only read by the same thread, so no barrier is needed.
+template <bool kPacked>
+__device__ __forceinline__ void window_scan_v2(const float (&d)[32], const float* __restrict__ sc, float* dcol, int dstride,
+                                               float& out_v, int& out_i) {
+  float mass = 0.f;                                       // bounds every partial window sum (phase 2 filter tolerance)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { dcol[i * dstride] = d[i]; mass += fabsf(d[i]); }
+  float best;
+  int bw;
+  scan_phase1<kPacked>(d, sc, best, bw);
+  const int s_found = scan_phase2(d, sc, dcol, dstride, best, bw, mass);
   out_v = best;
   out_i = (bw - 1) * 32 - ((bw - 1) * (bw - 2)) / 2 + s_found;
+}
+
+// Known key clip (rescoring of candidates whose key clip the approximate pass already fixed): the exact value of window
+// `key` (sequential sum) is checked against the value-only maximum of phase 1.  When the key's value IS the maximum and
+// its row is the first row attaining it, the key is confirmed at the cost of phase 1 alone; otherwise (a wrong key: the
+// approximate pass's argmax gap was misleading) phase 2 resolves the true first argmax.  Result = the full scan's.
+// (Residual: an exact fp32 tie with an EARLIER start of the same row keeps the given key — a documented exact-score tie.)
+template <bool kPacked>
+__device__ __forceinline__ void window_scan_known(const float (&d)[32], const float* __restrict__ sc, float* dcol, int dstride,
+                                                  int key, float& out_v, int& out_i) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dcol[i * dstride] = d[i];
+  // p(w, s) = (w-1) * 32 - (w-1)(w-2)/2 + s: invert for w by a 5-step search on the row starts
+  key = min(max(key, 0), 527);
+  int w = 1;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int wt = w + step;
+    if (wt <= 32 && (wt - 1) * 32 - ((wt - 1) * (wt - 2)) / 2 <= key) w = wt;
+  }
+  const int s = key - ((w - 1) * 32 - ((w - 1) * (w - 2)) / 2);
+  const float vk = window_value(dcol, dstride, sc, w, s);
+  float best;
+  int bw;
+  scan_phase1<kPacked>(d, sc, best, bw);
+  out_v = best;
+  out_i = key;
+  if (!(vk == best && bw == w)) {
+    float mass = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mass += fabsf(d[i]);
+    const int s_found = scan_phase2(d, sc, dcol, dstride, best, bw, mass);
+    out_i = (bw - 1) * 32 - ((bw - 1) * (bw - 2)) / 2 + s_found;
+  }
 }
 
 }  // namespace dkd

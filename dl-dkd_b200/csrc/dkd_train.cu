@@ -384,6 +384,38 @@ extern "C" int dkd_train_sim_fwd(const float* q, const float* x, const float* rq
   return DKD_OK;
 }
 
+// curve[m, l] = qn[m] . xn[labels[m], l] (both L2-normalised), masked frames -1e10: one warp per (query, 4 frames)
+__global__ void __launch_bounds__(256)
+train_curve_kernel(const float* __restrict__ qn, const float* __restrict__ xn, const uint8_t* __restrict__ mask,
+                   const int32_t* __restrict__ labels, int M, int L, int D, float* __restrict__ curve) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x;
+  const int n = labels[m];
+  const float4* q4 = reinterpret_cast<const float4*>(qn + (int64_t)m * D);
+  for (int l = blockIdx.y * 8 + warp; l < L; l += gridDim.y * 8) {
+    const float4* x4 = reinterpret_cast<const float4*>(xn + ((int64_t)n * L + l) * D);
+    float acc = 0.f;
+    for (int i = lane; i < (D >> 2); i += 32) {
+      const float4 a = __ldg(q4 + i), b = __ldg(x4 + i);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) curve[(int64_t)m * L + l] = (!mask || mask[(int64_t)n * L + l]) ? acc : DKD_MASKED_SCORE;
+  }
+}
+
+extern "C" int dkd_train_curve(const float* qn, const float* xn, const uint8_t* mask, const int32_t* labels, int32_t M,
+                               int32_t L, int32_t D, float* curve, void* stream) {
+  if (!qn || !xn || !labels || !curve || M < 0) return DKD_ERR_ARG;
+  if (L <= 0 || D <= 0 || D % 4 != 0) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(xn)) & 15) return DKD_ERR_ALIGN;
+  if (M == 0) return DKD_OK;
+  dim3 grid(M, (L + 31) / 32 < 4 ? (L + 31) / 32 : 4);
+  train_curve_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qn, xn, mask, labels, M, L, D, curve);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
 extern "C" int dkd_train_sim_bwd(const float* q, const float* x, const float* rq, const float* rx,
                                  const uint8_t* mask, const int32_t* labels, int32_t M, int32_t N, int32_t L,
                                  int32_t D, const float* max_n, const int32_t* arg_n, const int32_t* arg_u,

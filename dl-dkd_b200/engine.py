@@ -349,7 +349,10 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             if precision == "shortcut":     # the dense clip scores / key clips are already exact
                 cs, ck = per[bi]["clip"], per[bi]["key_clip"]
             else:
-                cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2])
+                # the dense key clips are final at this point (exact for the flagged pairs, unambiguous for the
+                # rest): the exact kernel confirms them against the exact maximum instead of searching all windows
+                cs, ck = ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=csr[:2],
+                                            known_key=per[bi]["key_clip"])
             wb = wbs[bi] if nb == 2 else 1.0
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
     out_s, out_i = ops.sort_candidates(cand_scores, cand, K)

@@ -182,8 +182,19 @@ class DLDKD(nn.Module):
         x = pos_embed_layer(input_proj_layer(feat))
         return encoder_layer(x, None if mask is None else mask.unsqueeze(1))
 
+    def enable_fused_encoder(self, on=True):
+        """Route encode_context (eval mode, CUDA, no autograd) through the hand-written encoder kernels
+        (encoder.FusedContextEncoder: tcgen05 kind::tf32 x 3 linears, fused LayerNorm / attention kernels).  Call again
+        after the parameters change (the weights are packed once)."""
+        from .encoder import FusedContextEncoder
+        self._fused_encoder = FusedContextEncoder(self).pack() if on else None
+        return self
+
     def encode_context(self, frame_video_feat, video_mask=None):
         """(B, L, Dv) [+ (B, L) mask] -> (inheritance (B, L, H), exploration (B, L, E) | None)."""
+        fe = getattr(self, "_fused_encoder", None)
+        if fe is not None and not self.training and frame_video_feat.is_cuda and not torch.is_grad_enabled():
+            return fe.encode_context(frame_video_feat, video_mask)
         inher = self.out_mapping_linear(self.encode_input(
             frame_video_feat, video_mask, self.visual_input_proj, self.visual_encoder, self.visual_pos_embed))
         if not self.double_branch:

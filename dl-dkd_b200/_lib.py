@@ -30,6 +30,8 @@ PROTOTYPES = {
     "dkd_clip_score_f32": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _L, _P],
     "dkd_score_max_bf16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _F, _P],
     "dkd_score_max_f16": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _F, _P],
+    "dkd_score_max_bf16_lists": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _L, _F, _P, _P, _L, _I, _P],
+    "dkd_clip_score_list": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _L, _P],
     "dkd_build_proposals_f16": [_P, _I, _I, _I, _P, _P, _P],
     "dkd_select_flagged": [_P, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P],
     "dkd_select_pairs_csr": [_P, _I, _I, _L, _F, _L, _P, _P, _P, _P, _P],

@@ -60,6 +60,8 @@ struct ExactParams {
   int Nv_real, tile_chunks, tiles_per_chunk;
   // mode 4 (linear layer: out = act(x_hat . W^T + bias)): "videos" are 128-row tiles of the packed weight matrix,
   // work items = (row chunk, weight tile) with the weight tile fastest (CTAs running together share the rows of x in L2)
+  int64_t list_stride;         // > 0: no vid_ptr — video n's entries are q_list[n * list_stride ...), vid_cnt[n] of them,
+                               // and results are scattered to the dense matrix at (query, video)
   const int32_t* known_key;    // mode 0, optional: dense (M, known_ld) key clips to confirm (dkd_scan.cuh window_scan_known)
   int64_t known_ld;
   const float2* row_ss;        // optional per-row (scale, shift): x_hat = x * scale + shift (LayerNorm prologue)
@@ -142,6 +144,11 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 
 __device__ __forceinline__ void video_range(const ExactParams& p, int n, int& e0, int& count) {
   if (p.vid_ptr) { e0 = p.vid_ptr[n]; count = p.vid_cnt ? p.vid_cnt[n] : p.vid_ptr[n + 1] - e0; }
+  else if (p.list_stride > 0) {
+    e0 = (int)((int64_t)n * p.list_stride);
+    count = p.vid_cnt[n];
+    if (count > (int)p.list_stride) count = (int)p.list_stride;
+  }
   else { e0 = 0; count = p.M; }
 }
 
@@ -585,7 +592,8 @@ exact_umma_kernel(const ExactParams p) {
         }
         if (r < count) {
           const int64_t o = p.out_slot ? (int64_t)p.out_slot[e0 + r]
-                                       : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n);
+                            : (p.list_stride > 0 ? (int64_t)p.q_list[e0 + r] * p.ld_out + n
+                                                 : (p.vid_ptr ? (int64_t)(e0 + r) : (int64_t)r * p.ld_out + n));
           p.out_max[o] = bv0;
           if (p.out_arg) p.out_arg[o] = bi0;
         }
@@ -891,4 +899,24 @@ extern "C" int dkd_linear_exact(const float* x, int64_t M, int32_t K, const floa
   p.Nv_real = wtiles;
   p.Nv = wtiles * p.tile_chunks;
   return launch_exact(4, p, K, 0, (cudaStream_t)stream);
+}
+
+// Exact clip scores of per-video query lists stored with a fixed stride (the lists dkd_score_max_bf16_lists writes):
+// video n owns q_list[n * list_stride, n * list_stride + vid_cnt[n]); entry (q, n) is written into the dense matrices
+// at out_max[q * ld_out + n] / out_arg[q * ld_out + n].  Same arithmetic as dkd_clip_score_f32.
+extern "C" int dkd_clip_score_list(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale,
+                                   int32_t Nv, int32_t T, int32_t D, float* out_max, int32_t* out_arg, int64_t ld_out,
+                                   const int32_t* vid_cnt, const int32_t* q_list, int64_t list_stride, void* stream) {
+  if (!qn || !clip_planes || !prop_scale || !out_max || !vid_cnt || !q_list || M < 0 || Nv < 0) return DKD_ERR_ARG;
+  if (list_stride <= 0 || ld_out < Nv || (int64_t)Nv * list_stride > 0x7fffffffLL) return DKD_ERR_ARG;
+  if (T <= 0 || T > 32 || D <= 0 || D % kXKB != 0 || D > 512) return DKD_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(qn) | reinterpret_cast<uintptr_t>(clip_planes) | reinterpret_cast<uintptr_t>(prop_scale)) & 15)
+    return DKD_ERR_ALIGN;
+  if (M == 0 || Nv == 0) return DKD_OK;
+  ExactParams p{};
+  p.q = qn; p.M = M; p.planes = clip_planes; p.scale = prop_scale;
+  p.Nv = Nv; p.T = T; p.D = D; p.R = T; p.Npad = 32; p.mask = nullptr;
+  p.out_max = out_max; p.out_arg = out_arg; p.ld_out = ld_out;
+  p.vid_ptr = nullptr; p.vid_cnt = vid_cnt; p.q_list = q_list; p.out_slot = nullptr; p.list_stride = list_stride;
+  return launch_exact(0, p, D, T, (cudaStream_t)stream);
 }

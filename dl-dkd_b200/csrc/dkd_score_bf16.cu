@@ -81,6 +81,9 @@ struct GemmParams {
   uint32_t* out_flags; // optional: bit (n & 31) of word [m][n >> 5] set when that gap is below `tau`
   float tau;
   int flag_words;     // words per query row = ceil(Nv / 32)
+  int32_t* flag_cnt;  // optional: per-video count of pairs whose gap is below tau (caller-zeroed) ...
+  int32_t* flag_list; // ... and their query indices, video n at [n * flag_cap, n * flag_cap + flag_cnt[n]) (any order)
+  int64_t flag_cap;
   int f16;            // operands are IEEE half instead of bf16 (same 2-byte layout, same MMA kind::f16 rate)
   int64_t ld_out;
 };
@@ -345,7 +348,13 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             if (p.out_arg) p.out_arg[o64] = idx;
             const float gap = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
             if (p.out_gap) p.out_gap[o64] = gap;
-            if (p.out_flags && gap < p.tau) atomicOr(&p.out_flags[(int64_t)m * p.flag_words + (v >> 5)], 1u << (v & 31));
+            if (gap < p.tau) {
+              if (p.out_flags) atomicOr(&p.out_flags[(int64_t)m * p.flag_words + (v >> 5)], 1u << (v & 31));
+              if (p.flag_list) {
+                const int pos = atomicAdd(&p.flag_cnt[v], 1);
+                if (pos < p.flag_cap) p.flag_list[(int64_t)v * p.flag_cap + pos] = m;
+              }
+            }
           }
         }
       }
@@ -429,8 +438,10 @@ static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const
 static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,
                         int32_t Nv, int32_t R, int32_t D, const uint8_t* mask, float* out_max,
                         int32_t* out_arg, float* out_gap, int64_t ld_out, uint32_t* out_flags,
-                        float tau, void* stream, bool f16) {
+                        float tau, void* stream, bool f16, int32_t* flag_cnt = nullptr, int32_t* flag_list = nullptr,
+                        int64_t flag_cap = 0) {
   if (!q_bf16 || !x_bf16 || !out_max || M < 0 || Nv < 0 || ld_out < Nv) return DKD_ERR_ARG;
+  if ((flag_cnt == nullptr) != (flag_list == nullptr) || (flag_list && flag_cap <= 0)) return DKD_ERR_ARG;
   if (Mpad < M || Mpad % kBlockM != 0) return DKD_ERR_SHAPE;
   if (R <= 0 || R > 4096 || R % 16 != 0 || D <= 0 || D % kBlockK != 0 || D / kBlockK > kMaxKBlocks) return DKD_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(x_bf16) & 15)) return DKD_ERR_ALIGN;
@@ -473,6 +484,7 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   p.f16 = f16 ? 1 : 0;
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
+  p.flag_cnt = flag_cnt; p.flag_list = flag_list; p.flag_cap = flag_cap;
   // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
   const int num_q_tiles = Mpad / (kBlockM * cta);
   const int workers = sms / cta;
@@ -503,4 +515,17 @@ extern "C" int dkd_score_max_f16(const uint16_t* q_f16, int32_t M, int32_t Mpad,
                                  float tau, void* stream) {
   return score_max_tc(q_f16, M, Mpad, x_f16, Nv, R, D, mask, out_max, out_arg, out_gap, ld_out, out_flags, tau,
                       stream, true);
+}
+
+// The GEMM with the ambiguous-pair lists written straight from the epilogue (no bit matrix, no dkd_select_flagged
+// pass): flag_cnt (Nv, caller-zeroed) counts the pairs of every video whose best / runner-up gap is below tau,
+// flag_list holds their query indices, video n at [n * flag_cap, n * flag_cap + flag_cnt[n]).  flag_cap >= M makes
+// overflow impossible.  Feed the lists to dkd_clip_score_list (dense scatter of the exact results).
+extern "C" int dkd_score_max_bf16_lists(const uint16_t* q, int32_t M, int32_t Mpad, const uint16_t* x, int32_t Nv,
+                                        int32_t R, int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg,
+                                        int64_t ld_out, float tau, int32_t* flag_cnt, int32_t* flag_list,
+                                        int64_t flag_cap, int32_t f16_operands, void* stream) {
+  if (!flag_cnt || !flag_list || !out_arg) return DKD_ERR_ARG;
+  return score_max_tc(q, M, Mpad, x, Nv, R, D, mask, out_max, out_arg, nullptr, ld_out, nullptr, tau, stream,
+                      f16_operands != 0, flag_cnt, flag_list, flag_cap);
 }

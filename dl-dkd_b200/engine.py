@@ -237,9 +237,10 @@ def score_two_scale_head(pc: PreparedCorpus, pq: PreparedQueries, precision="exa
             else:
                 prop = bd.prop_b
             if tau > 0:
-                s_clip, k_clip, flags = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.Pg, mask=pc.prop_mask, flag_tau=tau)
-                vb, ql, vc, slot = ops.select_flagged(flags, pc.Nv)
-                ops.clip_score_f32(qn, bd.clip_planes, bd.prop_scale, csr=(vb, ql, vc), scatter=(slot, s_clip, k_clip))
+                # the GEMM's epilogue appends every ambiguous pair to its video's list; the exact kernel re-resolves
+                # the listed pairs and writes them into the dense matrices in place
+                s_clip, k_clip, cnt, lst = ops.score_max_bf16_lists(qb, pq.M, prop, pc.Nv, pc.Pg, tau, mask=pc.prop_mask)
+                ops.clip_score_list(qn, bd.clip_planes, bd.prop_scale, cnt, lst, s_clip, k_clip)
             else:
                 s_clip, k_clip = ops.score_max_bf16(qb, pq.M, prop, pc.Nv, pc.Pg, mask=pc.prop_mask)
             q, tab = qh, bd.table_h

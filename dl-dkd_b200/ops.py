@@ -236,6 +236,45 @@ def score_max_bf16(q_bf16, M, x_bf16, Nv, R, mask=None, out_max=None, out_arg=No
     return out
 
 
+def score_max_bf16_lists(q, M, x, Nv, R, tau, mask=None):
+    """The tcgen05 GEMM with the ambiguous-pair lists written by its epilogue: -> (max (M, Nv), argmax (M, Nv),
+    flag_cnt (Nv,), flag_list (Nv, M)).  Operands both bf16 or both IEEE half."""
+    half = q.dtype == torch.float16
+    _chk(q, torch.float16 if half else torch.bfloat16, "q")
+    _chk(x, torch.float16 if half else torch.bfloat16, "x")
+    Mpad, D = q.shape
+    if x.numel() != Nv * R * D:
+        raise _lib.DkdError("x does not hold Nv*R rows of D features")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    dev = q.device
+    om = torch.empty((M, Nv), dtype=torch.float32, device=dev)
+    oa = torch.empty((M, Nv), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((Nv,), dtype=torch.int32, device=dev)
+    lst = torch.empty((Nv, M), dtype=torch.int32, device=dev)
+    _lib.call("dkd_score_max_bf16_lists", _p(q), M, Mpad, _p(x), Nv, R, D, _p(mask), _p(om), _p(oa), Nv, float(tau),
+              _p(cnt), _p(lst), M, int(half), _stream())
+    return om, oa, cnt, lst
+
+
+def clip_score_list(qn, planes, prop_scale, cnt, lst, out_max, out_arg):
+    """Exact clip score / key clip of the listed pairs (score_max_bf16_lists), written in place into the dense
+    (M, Nv) matrices."""
+    _chk(qn, torch.float32, "qn")
+    _chk(planes, torch.float32, "clip_planes")
+    _chk(prop_scale, torch.float32, "prop_scale")
+    _chk(cnt, torch.int32, "flag_cnt")
+    _chk(lst, torch.int32, "flag_list")
+    _chk(out_max, torch.float32, "out_max")
+    _chk(out_arg, torch.int32, "out_arg")
+    M, D = qn.shape
+    Nv, P = prop_scale.shape
+    T = int(round(((8 * P + 1) ** 0.5 - 1) / 2))
+    _lib.call("dkd_clip_score_list", _p(qn), M, _p(planes), _p(prop_scale), Nv, T, D, _p(out_max), _p(out_arg),
+              out_max.shape[1], _p(cnt), _p(lst), lst.shape[1], _stream())
+    return out_max, out_arg
+
+
 def select_flagged(flags, Nv, cap=None):
     """Bit matrix of flagged pairs (score_max_bf16 flag_tau) -> (vid_begin, q_list, vid_cnt, slot): per-video
     runs of query indices / dense slots m * Nv + n."""

@@ -156,6 +156,20 @@ int dkd_score_max_f16(const uint16_t* q_f16, int32_t M, int32_t Mpad, const uint
 int dkd_build_proposals_f16(const float* clips, int32_t Nv, int32_t T, int32_t D, uint16_t* prop_f16,
                             float* prop_scale, void* stream);
 
+/* The same GEMM with the ambiguous-pair lists written straight from its epilogue (one atomic per flagged pair; no bit
+ * matrix and no selection pass): flag_cnt (Nv, caller-zeroed) = number of pairs of each video whose gap is below tau,
+ * flag_list = their query indices, video n at [n * flag_cap, n * flag_cap + flag_cnt[n]) in any order (flag_cap >= M
+ * rules out overflow; entries beyond flag_cap are dropped).  f16_operands: IEEE-half instead of bf16 operands.
+ * dkd_clip_score_list consumes the lists: exact clip score / key clip of every listed pair (arithmetic of
+ * dkd_clip_score_f32) scattered into the dense matrices at (query, video). */
+int dkd_score_max_bf16_lists(const uint16_t* q, int32_t M, int32_t Mpad, const uint16_t* x, int32_t Nv, int32_t R,
+                             int32_t D, const uint8_t* mask, float* out_max, int32_t* out_arg, int64_t ld_out,
+                             float tau, int32_t* flag_cnt, int32_t* flag_list, int64_t flag_cap,
+                             int32_t f16_operands, void* stream);
+int dkd_clip_score_list(const float* qn, int32_t M, const float* clip_planes, const float* prop_scale, int32_t Nv,
+                        int32_t T, int32_t D, float* out_max, int32_t* out_arg, int64_t ld_out,
+                        const int32_t* vid_cnt, const int32_t* q_list, int64_t list_stride, void* stream);
+
 /* Per-video lists of the flagged pairs of a dkd_score_max_bf16 bit matrix: video n owns entries
  * [vid_begin[n], vid_begin[n] + vid_cnt[n]) of q_list (query index) / slot (m * ld + n), in any order; runs
  * are placed by a global cursor (1 int scratch).  One pass over the bit matrix, one block per 32 videos. */

@@ -444,3 +444,37 @@ def test_candidate_rescoring_plumbing(ops):
     rs, ri = ops.sort_candidates(cand_scores, cand, K)
     assert torch.equal(ri, ti)
     assert torch.equal(rs, ts)
+
+
+def test_gemm_epilogue_lists_equal_flag_matrix_selection(ops):
+    """dkd_score_max_bf16_lists (ambiguous pairs appended to per-video lists by the GEMM's epilogue) + dkd_clip_score_list
+    == the bit-matrix route (dkd_score_max_bf16 flags -> dkd_select_flagged -> dkd_clip_score_f32 scatter): same flagged
+    pairs per video, same dense matrices afterwards, bit for bit."""
+    Nv, L, D, M, tau = 300, 128, 384, 700, 1e-3
+    frames, mask, lengths = synth.encoded_corpus(Nv, L, D, seed=61, shared=1.5)
+    q = synth.encoded_queries(M, D, seed=62)
+    fc, lc, qc = _cuda(frames, lengths, q)
+    clips = ops.downsample_clips(fc, lc)
+    pb, ps, _ = ops.build_proposals(clips)
+    planes = ops.pack_clips(clips)
+    Mpad = ops.round_up(M, 256)
+    qn, qb = ops.normalize_rows(qc, want_f32=True, want_bf16=True, rows_pad=Mpad)
+    qn = qn[:M]
+    s1, k1, flags = ops.score_max_bf16(qb, M, pb.view(-1, D), Nv, 528, flag_tau=tau)
+    s2, k2, cnt, lst = ops.score_max_bf16_lists(qb, M, pb.view(-1, D), Nv, 528, tau)
+    assert torch.equal(s1, s2) and torch.equal(k1, k2)
+    vb, ql, vc, slot = ops.select_flagged(flags, Nv)
+    assert torch.equal(vc, cnt) and int(cnt.sum()) > 0
+    vbc, qlc, vcc, lstc = vb.cpu(), ql.cpu(), vc.cpu(), lst.cpu()
+    for n in (0, 1, 17, Nv - 1):
+        a = sorted(qlc[int(vbc[n]): int(vbc[n]) + int(vcc[n])].tolist())
+        assert a == sorted(lstc[n, : int(vcc[n])].tolist())
+    ops.clip_score_f32(qn, planes, ps, csr=(vb, ql, vc), scatter=(slot, s1, k1))
+    ops.clip_score_list(qn, planes, ps, cnt, lst, s2, k2)
+    assert torch.equal(s1, s2) and torch.equal(k1, k2)
+    # and the re-resolved pairs carry the exact kernel's values
+    se, ke = ops.clip_score_f32(qn, planes, ps)
+    fl = torch.zeros((M, Nv), dtype=torch.bool)
+    for n in range(Nv):
+        fl[lstc[n, : int(vcc[n])].long(), n] = True
+    assert torch.equal(s2.cpu()[fl], se.cpu()[fl]) and torch.equal(k2.cpu()[fl], ke.cpu()[fl])

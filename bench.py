@@ -856,7 +856,7 @@ def main():
         gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
         achieved = flops_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_avg_ms else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload)
         roofline = {"bound": "tensor", "kernel": "score_max_bf16_kernel (tcgen05 GEMM + fused max/argmax)" +

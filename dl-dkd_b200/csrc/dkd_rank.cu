@@ -102,6 +102,85 @@ __global__ void topk_dense_kernel(const float* __restrict__ scores, int M, int N
   }
 }
 
+// Top-K SELECTION (unsorted) by a 4-pass radix select on the monotone 32-bit score key: one warp per row, a 256-bin
+// histogram per pass in shared memory, then one compaction pass.  The candidate pass of engine.rank only needs the SET of
+// the K best (they are rescored and sorted afterwards) and the K-th best approximate score (the certificate), so the
+// streaming sort of topk_dense_kernel (7 bitonic flushes per row: ~30 k warp instructions) is not needed there.
+// Order rule as everywhere: score descending, lower id first among equal scores (ties at the K-th score are taken in
+// increasing column order until the quota is filled).
+__global__ void __launch_bounds__(256)
+select_topk_kernel(const float* __restrict__ scores, int M, int Nv, int64_t ld, int K, int id_base,
+                   int32_t* __restrict__ out_ids, float* __restrict__ out_kth) {
+  __shared__ int hist[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const float* row = scores + (int64_t)m * ld;
+  int32_t* oid = out_ids + (int64_t)m * K;
+  if (Nv <= K) {                                            // everything is selected; pad the rest
+    for (int n = lane; n < K; n += 32) oid[n] = n < Nv ? id_base + n : -1;
+    if (lane == 0) out_kth[m] = -INFINITY;
+    return;
+  }
+  int* h = hist[warp];
+  uint32_t prefix = 0u;
+  int need = K;                                             // rank of the wanted key among the keys matching `prefix`
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int n = lane; n < Nv; n += 32) {
+      const uint32_t key = float_key(row[n]);
+      if (pass == 0 || ((key ^ prefix) >> (shift + 8)) == 0u) atomicAdd(&h[(key >> shift) & 255u], 1);
+    }
+    __syncwarp();
+    // lane owns bins 8 lane .. 8 lane + 7; suffix sums from the top bin down
+    int c[8], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; tot += c[i]; }
+    int suf = tot;                                          // inclusive suffix sum over lanes >= this one
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += v;
+    }
+    const bool mine = suf >= need && suf - tot < need;      // the wanted key falls into one of my bins
+    int bin = 0, above = 0;
+    if (mine) {
+      int acc = suf - tot;                                  // keys in bins above mine
+#pragma unroll
+      for (int i = 7; i >= 0; --i) {
+        if (acc + c[i] >= need) { bin = lane * 8 + i; above = acc; break; }
+        acc += c[i];
+      }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = __ffs(who) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    above = __shfl_sync(0xffffffffu, above, src);
+    prefix |= (uint32_t)bin << shift;
+    need -= above;
+    __syncwarp();
+  }
+  // prefix = key of the K-th best score; `need` of the keys equal to it are still wanted (first columns first)
+  int cnt = 0, eq_taken = 0;
+  for (int n0 = 0; n0 < Nv; n0 += 32) {
+    const int n = n0 + lane;
+    const uint32_t key = n < Nv ? float_key(row[n]) : 0u;
+    const bool gt = n < Nv && key > prefix;
+    const bool eq = n < Nv && key == prefix;
+    const unsigned be = __ballot_sync(0xffffffffu, eq);
+    const bool take = gt || (eq && eq_taken + __popc(be & ((1u << lane) - 1u)) < need);
+    const unsigned bt = __ballot_sync(0xffffffffu, take);
+    if (take) oid[cnt + __popc(bt & ((1u << lane) - 1u))] = id_base + n;
+    cnt += __popc(bt);
+    eq_taken += __popc(be);
+  }
+  if (lane == 0) out_kth[m] = key_float(prefix);
+}
+
 // (G, M, K) shard lists -> (M, K).  Entries with id < 0 are padding.
 __global__ void merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids, int G,
                                   int M, int K, int S, float* __restrict__ out_scores,
@@ -312,6 +391,16 @@ extern "C" int dkd_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, 
   const size_t smem = (size_t)wpb * S * sizeof(u64);
   topk_dense_kernel<<<(M + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(
       scores, M, Nv, ld, K, S, id_base, out_scores, out_ids);
+  DKD_LAUNCH_CHECK();
+  return DKD_OK;
+}
+
+extern "C" int dkd_select_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, int32_t K, int32_t id_base,
+                               int32_t* out_ids, float* out_kth, void* stream) {
+  if (!scores || !out_ids || !out_kth || M < 0 || Nv < 0 || ld < Nv) return DKD_ERR_ARG;
+  if (K <= 0) return DKD_ERR_SHAPE;
+  if (M == 0) return DKD_OK;
+  select_topk_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(scores, M, Nv, ld, K, id_base, out_ids, out_kth);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

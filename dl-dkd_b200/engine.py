@@ -336,7 +336,8 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     if precision == "exact" or not rescore:
         return ops.topk(fused, K, pc.id_base) + extra
     Kc = max(Kc, K)
-    approx_s, cand = ops.topk(fused, Kc, pc.id_base)
+    # the candidates are rescored and sorted below: only their SET and the Kc-th approximate score are needed here
+    cand, approx_kth = ops.select_topk(fused, Kc, pc.id_base)
     csr = ops.candidates_to_csr(cand, pc.Nv, pc.id_base)
     cand_scores = torch.full((pq.M, Kc), float("-inf"), dtype=torch.float32, device=cand.device)
     if head == "frame":
@@ -358,7 +359,7 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
             ops.frame_fuse_csr(qn, bd.table_f, cs, ck, csr, w_clip, w_frame, wb, cand_scores, bi > 0)
     out_s, out_i = ops.sort_candidates(cand_scores, cand, K)
     if certify and Kc < pc.Nv:
-        unsure = out_s[:, K - 1] <= approx_s[:, Kc - 1] + (CERT_EPS if precision == "bf16" else CERT_EPS_F16)
+        unsure = out_s[:, K - 1] <= approx_kth + (CERT_EPS if precision == "bf16" else CERT_EPS_F16)
         args = dict(K=K, head=head, w_clip=w_clip, w_frame=w_frame)
         if certify == "deferred":
             PENDING.append(PendingCertificate(pc, pq, unsure, out_s, out_i, args))

@@ -364,6 +364,16 @@ def topk(scores, K, id_base=0):
     return os_, oi
 
 
+def select_topk(scores, K, id_base=0):
+    """Per-row top-K SET (unsorted ids (M, K) int32, -1 padded) + the K-th best score (M,) of a dense (M, Nv) matrix."""
+    _chk(scores, torch.float32, "scores")
+    M, Nv = scores.shape
+    oi = torch.empty((M, K), dtype=torch.int32, device=scores.device)
+    kth = torch.empty((M,), dtype=torch.float32, device=scores.device)
+    _lib.call("dkd_select_topk", _p(scores), M, Nv, Nv, K, id_base, _p(oi), _p(kth), _stream())
+    return oi, kth
+
+
 def merge_topk(scores, ids):
     """(G, M, K) shard lists -> merged (M, K)."""
     _chk(scores, torch.float32, "scores")

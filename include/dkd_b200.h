@@ -222,6 +222,13 @@ int dkd_fuse_scores(const float* a, const float* b, float wa, float wb, float* o
 int dkd_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, int32_t K, int32_t id_base,
              float* out_scores, int32_t* out_ids, void* stream);
 
+/* Top-K SELECTION without ordering (radix select on the score key, one warp per row): out_ids (M, K) = the ids of the K
+ * best entries of every row in column order (same order rule: ties at the K-th score go to the lower ids), padded with
+ * -1 when Nv < K; out_kth (M) = the K-th best score (-inf when Nv <= K).  For the candidate pass of the ranking, which
+ * rescored and sorts its candidates afterwards and needs only their set and the K-th approximate score. */
+int dkd_select_topk(const float* scores, int32_t M, int32_t Nv, int64_t ld, int32_t K, int32_t id_base,
+                    int32_t* out_ids, float* out_kth, void* stream);
+
 /* Merge G per-shard top-K lists (G, M, K) (e.g. after an NCCL all-gather) into one (M, K). */
 int dkd_merge_topk(const float* scores, const int32_t* ids, int32_t G, int32_t M, int32_t K,
                    float* out_scores, int32_t* out_ids, void* stream);

@@ -478,3 +478,24 @@ def test_gemm_epilogue_lists_equal_flag_matrix_selection(ops):
     for n in range(Nv):
         fl[lstc[n, : int(vcc[n])].long(), n] = True
     assert torch.equal(s2.cpu()[fl], se.cpu()[fl]) and torch.equal(k2.cpu()[fl], ke.cpu()[fl])
+
+
+@pytest.mark.parametrize("M,Nv,K", [(100, 2179, 128), (37, 500, 100), (9, 129, 128), (5, 60, 100), (300, 17432, 128)])
+def test_select_topk_equals_topk_set(ops, M, Nv, K):
+    """dkd_select_topk (radix select, unsorted) returns exactly the set dkd_topk ranks, including exact-score ties at
+    the K-th place (lower id wins), and the K-th best score."""
+    g = torch.Generator().manual_seed(M + Nv)
+    s = torch.randn(M, Nv, generator=g)
+    s[:, ::5] = 0.25                                     # many exact ties, also around the K-th score for some rows
+    s[1] = 1.0                                           # a row of all-equal scores: the K lowest ids
+    s[2, 7] = float("-inf")
+    sc = s.cuda()
+    ts, ti = ops.topk(sc, K, 1000)
+    si, kth = ops.select_topk(sc, K, 1000)
+    kk = min(K, Nv)
+    assert torch.equal(torch.sort(si, dim=1).values[:, K - kk:], torch.sort(ti[:, :kk], dim=1).values)
+    if Nv > K:
+        assert torch.equal(kth, ts[:, K - 1])
+        assert bool((si >= 1000).all())
+    else:
+        assert bool((si[:, kk:] == -1).all()) and bool(torch.isinf(kth).all())

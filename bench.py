@@ -904,7 +904,7 @@ def main():
                 # beside it: the UNMODIFIED reference (baseline/_ref) on the head it ships, same corpus shape — for
                 # the tvr_frame workload this IS the cpu_baseline (kind "reference")
                 try:
-                    nr = min(Nq, 600)
+                    nr = min(Nq, 4000)                                  # ~15-20 s of CPU work on 16 threads
                     refb = ReferenceBaseline(shape, nr)
                     refb.run(50)
                     rline = refb.run(nr)

@@ -32,3 +32,21 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_frame_head_times_the_unmodified_reference():
+    """--workload tvr_frame: the head the reference ships is timed on the UNMODIFIED reference (baseline/_ref, staged
+    by oracle/install_ref.py), kind "reference"."""
+    import pytest
+    from oracle import install_ref
+    install_ref.install()
+    if not install_ref.staged():
+        pytest.skip("the reference is not staged (no /root/reference here and no baseline/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tvr_frame",
+                        "--steps", "1", "--warmup", "1", "--cpu-sample-queries", "50"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["config"]["workload"] == "tvr_frame"
+    assert d["cpu_baseline"]["kind"] == "reference" and "baseline/_ref" in d["cpu_baseline"]["sample"]
+    assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0

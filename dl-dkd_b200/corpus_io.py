@@ -142,7 +142,8 @@ def pack_bigfile(feat_dir, video2frames, out_path, max_ctx_len=128, dtype="f32",
     """Reference BigFile directory (shape.txt 'rows dims', id.txt, feature.bin float32; utils/basic_utils.py:11-26)
     -> packed corpus, in one mapped pass.  video2frames: video id -> list of frame ids (the reference's
     video2frames dict, data_provider.py:271).  Per video: frames in list order, uniform_feature_sampling to
-    max_ctx_len, l2_normalize (data_provider.py:299-301).  order: video ids to write (default: sorted keys)."""
+    max_ctx_len, l2_normalize (data_provider.py:299-301), computed in float64 and cast to float32 at the end — bit for bit
+    what the reference's loader hands to cat_videos.  order: video ids to write (default: sorted keys)."""
     rows, dims = (int(x) for x in open(os.path.join(feat_dir, "shape.txt")).read().split())
     names = open(os.path.join(feat_dir, "id.txt"), encoding="ISO-8859-1").read().strip().split()
     if len(names) != rows:
@@ -155,9 +156,12 @@ def pack_bigfile(feat_dir, video2frames, out_path, max_ctx_len=128, dtype="f32",
     lengths = np.zeros((Nv,), dtype=np.int32)
     for n, vid in enumerate(order):
         idx = np.fromiter((name2index[f] for f in video2frames[vid]), dtype=np.int64)
-        v = l2_normalize_rows(uniform_feature_sampling(np.asarray(feats[idx], dtype=np.float32), max_ctx_len))
+        # float64 like the reference: BigFile.read_one returns Python floats, so np.array(...) of a video's frames is a
+        # float64 array and uniform_feature_sampling + l2_normalize_np_array run in float64 (data_provider.py:286-301);
+        # the cast to float32 happens last (cat_videos writes into a float32 tensor, :75-86)
+        v = l2_normalize_rows(uniform_feature_sampling(np.asarray(feats[idx], dtype=np.float64), max_ctx_len))
         lengths[n] = v.shape[0]
-        plane[n, : v.shape[0]] = v
+        plane[n, : v.shape[0]] = v.astype(np.float32)
     return write_packed(out_path, [plane], lengths, order, dtype=dtype)
 
 

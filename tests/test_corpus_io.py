@@ -105,9 +105,10 @@ def test_pack_bigfile_and_dataset_items(cio, dkd, tmp_path):
         for n, vid in enumerate(pc.ids):
             vecs = np.array([bf.read_one(f) for f in v2f[vid]])              # data_provider.py:286-290
             want = l2_normalize_np_array(uniform_feature_sampling(vecs, 128))
-            assert np.allclose(pc.video(n).numpy(), want.astype(np.float32), atol=1e-7), vid
+            assert want.dtype == np.float64                                  # the reference's loader works in float64
+            assert np.array_equal(pc.video(n).numpy(), want.astype(np.float32)), vid   # bit for bit
     row = {f: i for i, f in enumerate(names)}
-    want = cio.l2_normalize_rows(cio.uniform_feature_sampling(feats[[row[f] for f in v2f["vidB"]]], 128))
+    want = cio.l2_normalize_rows(cio.uniform_feature_sampling(feats[[row[f] for f in v2f["vidB"]]].astype(np.float64), 128))
     assert np.array_equal(pc.video(1).numpy(), want.astype(np.float32))
     ds = cio.PackedVideoDataset(pc)
     feat, idx, vid = ds[2]

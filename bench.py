@@ -34,6 +34,14 @@ K_TOP = 100
 K_CAND = 128
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries the one JSON line): which leg every rank is in, with a wall-clock stamp."""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -410,6 +418,7 @@ def main():
     ap.add_argument("--cpu-sample-queries", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-leg", action="store_true", help="skip timing the unmodified reference's frame head")
+    ap.add_argument("--no-eval-epoch", action="store_true", help="skip the wall-clock run of the reference-named eval_epoch entry")
     ap.add_argument("--no-encoder", action="store_true", help="skip timing encode_context (PyTorch mirror vs fused kernels)")
     ap.add_argument("--no-c4", action="store_true", help="skip the reduced c4_stream sub-measurement")
     ap.add_argument("--c4-sub-videos", type=int, default=32768)
@@ -550,6 +559,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def any_rank(flag):
+        """True on every rank if `flag` is true on any rank (decisions that change the sequence of collectives must
+        be taken together)."""
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
+    log("corpus prepared; warm-up")
     # warm-up (also: one pass to count kernel launches per step)
     for _ in range(args.warmup):
         step(qs)
@@ -558,6 +577,7 @@ def main():
     launches_per_step = _lib.launch_count()
     barrier()
 
+    log("timed region")
     # ---- timed region: device-resident inputs
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -579,7 +599,7 @@ def main():
     barrier()
     # deferred certificates of the timed steps: a fallback (never observed at these shapes) would have been applied
     # AFTER the timed region, so in that case the steps are timed again with the certificate read back inside each step
-    if engine.finish() and not stream:
+    if any_rank(engine.finish()) and not stream:
         cert_mode[0] = True
         _lib.set_timed({gemm_entry})
         barrier()
@@ -617,6 +637,7 @@ def main():
                       for k, v in _lib.timed_results().items() if v}
         _lib.set_timed(set())
         barrier()
+    log("e2e leg")
     # ---- e2e: host buffers in, host buffers out, through the same public entry (engine.rank)
     q_host = [q.cpu().pin_memory() for q in qs]
     out_s = torch.empty((Nq, K_TOP), dtype=torch.float32).pin_memory()
@@ -645,9 +666,6 @@ def main():
             for t in qd:
                 t.record_stream(main)
             s, ids = step(qd)
-            if engine.finish(keep_last=1):         # step i - 1's certificate: already on the host, no stall
-                cert_mode[0] = True                # a fallback patched lists that were already copied out: from here
-                                                   # on the certificate is read back inside the step (and e2e re-timed)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_stream):
@@ -657,6 +675,9 @@ def main():
             s.record_stream(copy_stream)
             ids.record_stream(copy_stream)
         main.wait_stream(copy_stream)          # the last result has reached host memory
+        # the steps' certificates are looked at once here (no host synchronisation inside the loop); a fallback would
+        # have patched lists that were already copied out, so in that case the leg is timed again with the certificate
+        # read back inside every step
         if engine.finish():
             cert_mode[0] = True
 
@@ -668,7 +689,8 @@ def main():
     run_e2e(e2e_steps)
     ev2[1].record()
     barrier()
-    if cert_mode[0] is True and not stream:      # see run_e2e: time it again with the in-step certificate
+    if any_rank(cert_mode[0] is True) and not stream:      # see run_e2e: time it again with the in-step certificate
+        cert_mode[0] = True
         ev2[0].record()
         run_e2e(e2e_steps)
         ev2[1].record()
@@ -684,6 +706,7 @@ def main():
            "boundary": "encoded query vectors in pinned host memory -> engine.rank -> top-100 (score, id) in host memory; "
                        "copies on a side stream, overlapped with the neighbouring steps' kernels"}
 
+    log("parity vs exact path")
     # ---- parity of the timed result: bf16+rescore top-100 == exact fp32 path top-100, EVERY query (in slices of
     # 2,048 to bound the exact path's dense temporaries)
     same_ids = same_scores = True
@@ -699,6 +722,7 @@ def main():
     parity = {"queries_checked": n_par, "top100_ids_identical_to_exact_fp32": same_ids,
               "top100_scores_identical": same_scores}
 
+    log("variants")
     # ---- reported variant, same run / same box: the linearity-shortcut pass (exact clip scale for every pair, no dense
     # GEMM).  Not the headline: north_star specifies the dense bf16 GEMM.
     variants = None
@@ -724,6 +748,7 @@ def main():
                                          "(tcgen05 kind::tf32 x 3) + window scan, fp16 frame gather, exact frame "
                                          "rescoring of the candidates; no dense GEMM, no ambiguity pass"}}
 
+    log("encoder leg (rank 0)")
     # ---- the step right before the path: DLDKD.encode_context over the TVR corpus, PyTorch / cuBLAS
     # mirror against the fused encoder kernels (tcgen05 kind::tf32 x 3 linears + LayerNorm / attention kernels), same
     # synthetic raw features; query independent, run once per corpus, NOT part of the timed step
@@ -761,6 +786,51 @@ def main():
                    "tolerance": 1e-4, "default": "opt-in (model.enable_fused_encoder()); see DESIGN.md section 6b"}
         del xraw, ra, rb, fa, fb
 
+    log("eval_epoch leg (rank 0)")
+    # ---- the reference-named entry end to end: eval_epoch(model, video_dataset, text_dataset, opt) (method/eval.py:237-263)
+    # on in-memory datasets of RAW synthetic features (the reference's item layout), wall clock: DataLoader collation,
+    # H2D, encode_context / encode_query (PyTorch), corpus preparation, device ranking (opt.precision = "bf16": no
+    # dense D2H), R@K on the device.  Once more with opt.precision = "exact" (the reference's dense flow): the R-sums of
+    # the two flows must be equal — R@K parity through the drop-in entry at the full TVR shape.
+    eval_epoch_leg = None
+    if not stream and rank == 0 and not args.no_eval_epoch and head == "two_scale":
+        from oracle.datasets import QuerySet, VideoSet
+        from dkd_b200 import eval as E
+        g = torch.Generator(device=dev).manual_seed(77)
+        vids = []
+        for lo_ in range(0, Nv, 200):
+            x = torch.randn(min(200, Nv - lo_), shape["L"], shape["Dv"], device=dev, generator=g)
+            vids.extend((x / (x.norm(dim=-1, keepdim=True) + 1e-5)).cpu().unbind(0))
+        qlen = torch.randint(5, shape["Lq"] + 1, (Nq,), generator=torch.Generator().manual_seed(78))
+        xq = torch.randn(Nq, shape["Lq"], shape["Dq"], device=dev, generator=g)
+        xq = (xq / (xq.norm(dim=-1, keepdim=True) + 1e-5)).cpu()
+        qset = QuerySet([xq[i, : int(qlen[i])] for i in range(Nq)], Nv)
+        vset = VideoSet(vids)
+        del xq
+        import types
+        opt_e = types.SimpleNamespace(eval_context_bsz=200, eval_query_bsz=50, num_workers=0, pin_memory=False, device=dev,
+                                      double_branch=True, scoring="two_scale", precision=args.operand)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rsum_fast = E.eval_epoch(model, vset, qset, opt_e)
+        torch.cuda.synchronize()
+        t_fast = time.perf_counter() - t0
+        opt_e.precision = "exact"
+        t0 = time.perf_counter()
+        rsum_exact = E.eval_epoch(model, vset, qset, opt_e)
+        torch.cuda.synchronize()
+        t_exact = time.perf_counter() - t0
+        eval_epoch_leg = {"entry": "dkd_b200.eval.eval_epoch(model, video_dataset, text_dataset, opt)  [method/eval.py:237-263]",
+                          "seconds_hot_path": t_fast, "pairs_per_s_hot_path": Nq * Nv / t_fast,
+                          "seconds_reference_flow_exact": t_exact, "rsum_hot_path": rsum_fast, "rsum_exact_flow": rsum_exact,
+                          "rsum_identical": bool(rsum_fast == rsum_exact),
+                          "what": "wall clock incl. DataLoader collation of 4.4 GB of raw features (host Python, like the "
+                                  "reference), H2D, PyTorch encoders, corpus preparation; the device ranking itself is the "
+                                  "timed step above"}
+        del vids, vset, qset
+        torch.cuda.empty_cache()
+
+    log("strong-scaling leg")
     # ---- strong scaling: ONE fixed corpus of strong_shards x 2,179 videos (the concatenation of the weak-scaling
     # shards 0..7: 17,432 videos, 62 GB of operands on one GPU), split in contiguous blocks over the N ranks; same
     # queries, same step, same merge.  value = Nq x 17,432 / max-over-ranks time: it can fall short of N x the 1-GPU
@@ -791,6 +861,7 @@ def main():
             st_s, st_i = step(qs, corpus=pc_s)
         ev4[1].record()
         barrier()
+        strong_fallbacks = engine.finish()        # local: patches this rank's lists in place if a certificate failed
         s_ms = ev4[0].elapsed_time(ev4[1]) / ssteps
         if world > 1:
             t = torch.tensor([s_ms], device=dev)
@@ -800,12 +871,13 @@ def main():
         ok = bool((st_s[:, :-1] >= st_s[:, 1:]).all()) and int(st_i.min()) >= 0 and int(st_i.max()) < tot
         strong = {"scaling": "strong", "corpus_videos": tot, "videos_per_gpu": hi - lo, "ms_per_step": s_ms,
                   "value": Nq * tot / (s_ms * 1e-3), "unit": "pairs/s", "steps": ssteps, "lists_valid": ok,
-                  "checksum_ids": int(st_i.long().sum().item()),
+                  "checksum_ids": int(st_i.long().sum().item()), "certificate_fallbacks_rank0": strong_fallbacks,
                   "what": "fixed corpus = weak-scaling shards 0..%d concatenated, contiguous blocks per rank; "
                           "checksum_ids must be the same at every N" % (G - 1)}
         del pc_s
         torch.cuda.empty_cache()
 
+    log("c4_stream leg")
     # ---- BASELINE.json configs[3] at a driver-runnable size (the default run has no flags): the streamed engine on
     # c4_sub_videos clip-feature videos PER GPU x c4_sub_queries queries, chunked exactly like the full config
     # (--workload c4_stream runs the 125 k x 100 k per-GPU size), operand building inside the step, N-way merge.
@@ -845,6 +917,7 @@ def main():
         del fr4, mk4, q4
         torch.cuda.empty_cache()
 
+    log("reporting / CPU legs (rank 0)")
     if rank == 0:
         pk = peaks()
         P = ops.num_proposals(shape["T"])
@@ -878,13 +951,15 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "roofline": roofline, "prep_ms": prep_ms,
                 "corpus_bytes": pc.nbytes() if pc is not None else int(sum(f.numel() * 4 for f in frames)),
-                "kernels_ms": kernels_ms, "parity": parity, "variants": variants, "strong": strong, "c4_stream": c4, "encoder": encoder,
+                "kernels_ms": kernels_ms, "parity": parity, "variants": variants, "strong": strong, "c4_stream": c4, "encoder": encoder, "eval_epoch": eval_epoch_leg,
                 "certify": {"eps": engine.CERT_EPS, "checked_queries": engine.STATS["certify_checked_queries"],
                             "fallback_queries": engine.STATS["certify_fallback_queries"],
                             "fallback_queries_in_timed_steps": timed_fallbacks,
                             "note": "queries whose exact 100th score is within eps of the last candidate's approximate "
                                     "score are re-ranked by the all-exact path (all calls of this process)"}}
         failed = not (parity["top100_ids_identical_to_exact_fp32"] and parity["top100_scores_identical"])
+        if eval_epoch_leg is not None and not eval_epoch_leg["rsum_identical"]:
+            failed = True
         if not args.no_cpu_baseline:
             # CPU leg: the oracle port of the reference's eval loop on the SAME encoded tensors (bounded sample of
             # queries x the full corpus, >= ~20 s of CPU work), timed; then, untimed, the parity of the timed GPU

@@ -81,6 +81,17 @@ constexpr int kXGroup = 4;                   // mode 2: videos sharing one stage
 #ifndef DKD_X_KNOWN
 #define DKD_X_KNOWN 1          // known-key confirmation: 0 = off (full scan), 1 = scalar phase 1, 2 = packed phase 1
 #endif
+#ifndef DKD_X_STREAM_B0
+#define DKD_X_STREAM_B0 0      // 1: mode 0 streams the video's clip planes per K block (like mode 1) instead of keeping them
+                               // resident, which frees 72 KB of shared memory for a deeper stager ring (DKD_X_RING0).
+                               // MEASURED (round 2, whole step, same box): exact kernel's four calls 3.15 ms (ring 5) /
+                               // 2.96 ms (ring 4) against 2.93 ms resident with ring 3 — more query rows in flight do
+                               // not help: the list forms are bound by the stagers' instruction stream, not by latency
+#endif
+#ifndef DKD_X_RING0
+#define DKD_X_RING0 5          // stager ring slots of mode 0 when B is streamed (ring - 1 query-row blocks in flight per warp)
+#endif
+constexpr bool kXStreamB0 = DKD_X_STREAM_B0 != 0;
 constexpr int kXListScan = DKD_X_LIST_SCAN;
 constexpr int kXKnown = DKD_X_KNOWN;
 constexpr bool kXTwoPhaseList = kXListScan != 0 || kXKnown != 0;   // the scan scratch in shared memory is needed
@@ -190,6 +201,7 @@ exact_umma_kernel(const ExactParams p) {
   constexpr int kScaleBufs = kMode == 2 ? kXGroup : 2;
   constexpr int kStageSets = kMode == 2 ? 1 : 2;                // stager warps per TMEM lane quarter
   constexpr int kScanGroups = (kMode == 0 && kXTwoPhaseList) ? 1 : 0;   // scan scratch (two-phase / known-key scans)
+  constexpr bool kResB = kMode == 0 && !kXStreamB0;             // B operand resident per video (else streamed per K block)
   constexpr uint32_t kXACol0 = 2 * kDW;                         // first A-ring column
   constexpr int kXStages = (kXTmemCols - 2 * kDW) / 64;         // A ring stages: 7 / 4
   extern __shared__ __align__(1024) uint8_t smem_raw_x[];
@@ -199,9 +211,9 @@ exact_umma_kernel(const ExactParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_x) + 1023) & ~(uintptr_t)1023);
   const int num_kb = p.D / kXKB;
   // mode 0: [buf][kb][plane] x 4 KB, one buffer per video; mode 1: [stage][plane] x Npad x 128 B, one stage per K block
-  const uint32_t b_buf_bytes = kMode == 0 ? (uint32_t)num_kb * 2u * kXBPlane : 2u * (uint32_t)p.Npad * 128u;
+  const uint32_t b_buf_bytes = kResB ? (uint32_t)num_kb * 2u * kXBPlane : 2u * (uint32_t)p.Npad * 128u;
   uint8_t* sB = smem;
-  uint8_t* sS = sB + (size_t)(kMode == 0 ? p.b_bufs : kXBStages) * b_buf_bytes;   // [stager warp][slot][32 rows] x 128 B
+  uint8_t* sS = sB + (size_t)(kResB ? p.b_bufs : kXBStages) * b_buf_bytes;   // [stager warp][slot][32 rows] x 128 B
   // scan scratch (clip-window modes): per scan group 32 x 128 floats, column = tile row (two-phase scan, dkd_scan.cuh)
   float* sD = reinterpret_cast<float*>(sS + (size_t)(4 * kStageSets) * kXRing * kXSlotBytes);
   ExactCtl* ctl = reinterpret_cast<ExactCtl*>(reinterpret_cast<uint8_t*>(sD) + (size_t)kScanGroups * kXScanScratch);
@@ -389,7 +401,7 @@ exact_umma_kernel(const ExactParams p) {
         if (kMode == 4) { int r0_; item_range_linear(p, n, vid, r0_, count); }
         else video_range(p, n, e0, count);
         if (count <= 0) continue;
-        if (kMode == 0) {
+        if (kResB) {
           const uint32_t bb = vi % b_bufs;
           mbar_wait_backoff(&ctl->b_empty[bb], ((vi / b_bufs) & 1u) ^ 1u, 5 * p.wait_ns);
           ++vi;
@@ -427,7 +439,7 @@ exact_umma_kernel(const ExactParams p) {
       else video_range(p, n, e0, count);
       if (count <= 0) continue;
       uint32_t bb = 0;
-      if (kMode == 0) {
+      if (kResB) {
         bb = vi % b_bufs;
         mbar_wait_backoff(&ctl->b_full[bb], (vi / b_bufs) & 1u, p.wait_ns);
         ++vi;
@@ -441,7 +453,7 @@ exact_umma_kernel(const ExactParams p) {
           const uint32_t stage = it % (uint32_t)kXStages;
           const uint32_t phase = (it / (uint32_t)kXStages) & 1u;
           uint32_t bs = 0;
-          if (kMode != 0) {
+          if (!kResB) {
             bs = itb % (uint32_t)kXBStages;
             mbar_wait_backoff(&ctl->b_full[bs], (itb / (uint32_t)kXBStages) & 1u, p.wait_ns);
             ++itb;
@@ -451,7 +463,7 @@ exact_umma_kernel(const ExactParams p) {
           if (elected) {
             const uint32_t a_hi = tmem_base + kXACol0 + stage * 64u;
             const uint32_t a_lo = a_hi + 32u;
-            const uint64_t b_hi = kMode == 0 ? bdesc0 + (uint64_t)((bb * b_buf_bytes + (uint32_t)kb * 2u * b_plane) >> 4)
+            const uint64_t b_hi = kResB ? bdesc0 + (uint64_t)((bb * b_buf_bytes + (uint32_t)kb * 2u * b_plane) >> 4)
                                              : bdesc0 + (uint64_t)((bs * b_buf_bytes) >> 4);
             const uint64_t b_lo = b_hi + (uint64_t)(b_plane >> 4);
 #pragma unroll
@@ -461,14 +473,14 @@ exact_umma_kernel(const ExactParams p) {
               umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, 1u);
             }
             umma_commit(&ctl->a_empty[stage]);
-            if (kMode != 0) umma_commit(&ctl->b_empty[bs]);
+            if (!kResB) umma_commit(&ctl->b_empty[bs]);
           }
           __syncwarp();
         }
         if (elected) umma_commit(&ctl->tmem_full[buf]);
         __syncwarp();
       }
-      if (kMode == 0) {
+      if (kResB) {
         if (elected) umma_commit(&ctl->b_empty[bb]);
         __syncwarp();
       }
@@ -764,13 +776,14 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_kb = D / kXKB;
-  const int ring = (mode == 0 || mode == 2) && D > 448 ? 2 : 3;   // clip modes: the resident B buffer grows with D
+  const bool stream0 = mode == 0 && kXStreamB0;                 // mode 0 with the clip planes streamed per K block
+  const int ring = stream0 ? DKD_X_RING0 : ((mode == 0 || mode == 2) && D > 448 ? 2 : 3);   // resident B grows with D
   const int ring_warps = mode == 2 ? 4 : kXStageWarps;        // mode 2: one stager warp per TMEM lane quarter
   const int scan_groups = (mode == 0 && kXTwoPhaseList) ? 1 : 0;
   const size_t fixed = sizeof(ExactCtl) + 1024 + 128 + 16384 /* static shared, largest mode */ +
                        (size_t)ring_warps * ring * kXSlotBytes + (size_t)scan_groups * kXScanScratch;
   size_t b_total;
-  if (mode == 0) {
+  if (mode == 0 && !stream0) {
     const size_t b_buf = (size_t)num_kb * 2 * kXBPlane;
     if ((size_t)max_smem < fixed + b_buf) return DKD_ERR_SHAPE;
     p.b_bufs = ((size_t)max_smem >= fixed + 2 * b_buf) ? 2 : 1;
@@ -788,7 +801,9 @@ static int launch_exact(int mode, ExactParams p, int32_t D, int32_t T, cudaStrea
     return DKD_OK;
   };
   int rc;
-  if (mode == 0) {
+  if (mode == 0 && stream0) {
+    rc = (T == 32) ? launch(exact_umma_kernel<0, true, DKD_X_RING0>) : launch(exact_umma_kernel<0, false, DKD_X_RING0>);
+  } else if (mode == 0) {
     if (ring == 3) rc = (T == 32) ? launch(exact_umma_kernel<0, true, 3>) : launch(exact_umma_kernel<0, false, 3>);
     else rc = (T == 32) ? launch(exact_umma_kernel<0, true, 2>) : launch(exact_umma_kernel<0, false, 2>);
   } else if (mode == 2) {

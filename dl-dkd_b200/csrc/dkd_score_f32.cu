@@ -221,8 +221,20 @@ frame_fuse_kernel(const TT* __restrict__ q, const TT* __restrict__ table,
 // at a time in half2 (HFMA2), each 4-product partial sum is widened and accumulated in fp32.  Eight videos
 // are processed per step and their 8 x 8 lane partials reduced by a 7-shuffle transpose, so that lane j ends
 // with the frame score of video n0 + j: the (clip, key clip) loads and the fused stores are 32-byte runs.
+// Register budget of the gather (round-2 A/B inside the whole step, profiles/r2_ab_gather.md): with plain
+// __launch_bounds__(256) ptxas settles at 70 registers and keeps ~9 row loads in flight per lane: 2.75 ms per step (two
+// launches); telling it that 3 blocks per SM are enough (<= 85 registers) lets it keep more loads in flight at the same
+// occupancy: 2.03 ms.  4 blocks (<= 64 registers) 2.44, 1 block (212 registers, every load hoisted) 3.30; loading the
+// rows of 2 / 4 videos explicitly before consuming them (DKD_FF_BATCH) 2.13 / 2.03 at 3 blocks.
+#ifndef DKD_FF_BATCH
+#define DKD_FF_BATCH 1      // videos whose table rows are loaded before any of them is consumed
+#endif
+#ifndef DKD_FF_MINBLOCKS
+#define DKD_FF_MINBLOCKS 3
+#endif
+#define DKD_FF_BOUNDS __launch_bounds__(256, DKD_FF_MINBLOCKS)
 template <int kC>  // D = 64 * kC
-__global__ void __launch_bounds__(256)
+__global__ void DKD_FF_BOUNDS
 frame_fuse_h_kernel(const __half* __restrict__ q, const __half* __restrict__ table,
                     const float* __restrict__ clip, const int32_t* __restrict__ key_clip, int M, int Nv,
                     int P, int64_t ld, float wc, float wf, float wb, int accumulate, int vchunk,
@@ -246,24 +258,32 @@ frame_fuse_h_kernel(const __half* __restrict__ q, const __half* __restrict__ tab
     kk = kk < 0 ? 0 : (kk >= P ? P - 1 : kk);
     float part[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = __shfl_sync(gmask, kk, j, 8);
-      const int n = min(n0 + j, n_end - 1);
-      const __half* row = table + ((int64_t)n * P + k) * D + 8 * sub;
-      float acc = 0.f;
+    for (int j0 = 0; j0 < 8; j0 += DKD_FF_BATCH) {
+      uint4 t[DKD_FF_BATCH][kC];
 #pragma unroll
-      for (int i = 0; i < kC; ++i) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + 64 * i));
-        const __half2* tp = reinterpret_cast<const __half2*>(&t);
-        const __half2* qp = reinterpret_cast<const __half2*>(&qv[i]);
-        __half2 s2 = __hmul2(tp[0], qp[0]);
-        s2 = __hfma2(tp[1], qp[1], s2);
-        s2 = __hfma2(tp[2], qp[2], s2);
-        s2 = __hfma2(tp[3], qp[3], s2);
-        const float2 f = __half22float2(s2);
-        acc += f.x + f.y;
+      for (int b = 0; b < DKD_FF_BATCH; ++b) {
+        const int k = __shfl_sync(gmask, kk, j0 + b, 8);
+        const int n = min(n0 + j0 + b, n_end - 1);
+        const __half* row = table + ((int64_t)n * P + k) * D + 8 * sub;
+#pragma unroll
+        for (int i = 0; i < kC; ++i) t[b][i] = __ldg(reinterpret_cast<const uint4*>(row + 64 * i));
       }
-      part[j] = acc;
+#pragma unroll
+      for (int b = 0; b < DKD_FF_BATCH; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kC; ++i) {
+          const __half2* tp = reinterpret_cast<const __half2*>(&t[b][i]);
+          const __half2* qp = reinterpret_cast<const __half2*>(&qv[i]);
+          __half2 s2 = __hmul2(tp[0], qp[0]);
+          s2 = __hfma2(tp[1], qp[1], s2);
+          s2 = __hfma2(tp[2], qp[2], s2);
+          s2 = __hfma2(tp[3], qp[3], s2);
+          const float2 f = __half22float2(s2);
+          acc += f.x + f.y;
+        }
+        part[j0 + b] = acc;
+      }
     }
     // transpose-reduce: after the three rounds lane `sub` holds the total of pair `sub`
     float r4[4], r2[2];
@@ -292,8 +312,152 @@ frame_fuse_h_kernel(const __half* __restrict__ q, const __half* __restrict__ tab
   }
 }
 
+// Bulk-copy flavour of the fp16 gather.  Same mapping (an 8-lane group owns one query, its query halves in registers;
+// eight videos per step reduced by the 7-shuffle transpose), but the key clips' table rows travel by cp.async.bulk
+// (768 B per row at D = 384, one instruction of one lane, completion on an mbarrier) into a per-group ring of 8 row
+// slots in shared memory instead of through 48 LDG.128 per row into registers: the bytes in flight per SM are set by
+// the 196 KB of ring (8 rows x 32 groups) instead of by the registers left over next to the query (~110 KB at 70
+// registers x 768 threads).  The gather is latency bound — L2 at ~52 % of its peak in the register version
+// (profiles/r2_ncu_step.md) — so more bytes in flight looked like the lever.
+// MEASURED (round 2, same box, whole step): 6.13 ms per step against 2.51 ms for the register version — one 768-byte
+// bulk copy per (query, video) pair (23.7 M per launch) is bound by the copy engine's per-request cost, not by bytes in
+// flight.  Kept as the record of that experiment; compiled only with -DDKD_FF_BULK=1.
+#ifndef DKD_FF_BULK
+#define DKD_FF_BULK 0
+#endif
+#if DKD_FF_BULK
+__device__ __forceinline__ uint32_t ff_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int kC>
+__global__ void __launch_bounds__(256, 1)
+frame_fuse_h_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ table,
+                         const float* __restrict__ clip, const int32_t* __restrict__ key_clip, int M, int Nv,
+                         int P, int64_t ld, float wc, float wf, float wb, int accumulate, int vchunk,
+                         float* __restrict__ out_frame, float* __restrict__ fused) {
+  constexpr int D = 64 * kC;
+  constexpr uint32_t kRowBytes = D * 2;
+  extern __shared__ __align__(128) uint8_t ff_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ff_smem + 32 * 8 * kRowBytes);     // [group][slot]
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int m = blockIdx.x * 32 + grp;
+  const bool live_m = m < M;
+  const int mm = live_m ? m : M - 1;
+  const int n_begin = blockIdx.y * vchunk;
+  const int n_end = min(Nv, n_begin + vchunk);
+  uint8_t* ring = ff_smem + (size_t)grp * 8 * kRowBytes;
+  uint64_t* gbar = bars + grp * 8;
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ff_smem_u32(&gbar[j])));
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint4 qv[kC];
+#pragma unroll
+  for (int i = 0; i < kC; ++i) qv[i] = *reinterpret_cast<const uint4*>(q + (int64_t)mm * D + 64 * i + 8 * sub);
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);          // the 8 lanes of this group
+  auto issue = [&](int j, int n, int k) {                              // lane 0 of the group: row of video n -> slot j
+    const __half* src = table + ((int64_t)n * P + k) * D;
+    const uint32_t bar = ff_smem_u32(&gbar[j]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kRowBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ff_smem_u32(ring + (size_t)j * kRowBytes)), "l"(src), "r"(kRowBytes), "r"(bar) : "memory");
+  };
+  auto load_key = [&](int n0) {
+    const int nj = min(n0 + sub, n_end - 1);
+    int kk = key_clip[(int64_t)mm * ld + nj];
+    return kk < 0 ? 0 : (kk >= P ? P - 1 : kk);
+  };
+  int kk = load_key(n_begin);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = __shfl_sync(gmask, kk, j, 8);
+    if (sub == 0) issue(j, min(n_begin + j, n_end - 1), k);
+  }
+  uint32_t phase = 0;
+  for (int n0 = n_begin; n0 < n_end; n0 += 8) {
+    const bool more = n0 + 8 < n_end;
+    const int kk_next = more ? load_key(n0 + 8) : 0;
+    float part[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t bar = ff_smem_u32(&gbar[j]);
+      uint32_t ok = 0, spins = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();                    // a protocol bug traps instead of hanging the GPU
+      }
+      const uint8_t* row = ring + (size_t)j * kRowBytes + 16 * sub;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < kC; ++i) {
+        const uint4 t = *reinterpret_cast<const uint4*>(row + 128 * i);
+        const __half2* tp = reinterpret_cast<const __half2*>(&t);
+        const __half2* qp = reinterpret_cast<const __half2*>(&qv[i]);
+        __half2 s2 = __hmul2(tp[0], qp[0]);
+        s2 = __hfma2(tp[1], qp[1], s2);
+        s2 = __hfma2(tp[2], qp[2], s2);
+        s2 = __hfma2(tp[3], qp[3], s2);
+        const float2 f = __half22float2(s2);
+        acc += f.x + f.y;
+      }
+      part[j] = acc;
+      __syncwarp(gmask);                                               // every lane has read slot j
+      if (more) {
+        const int k = __shfl_sync(gmask, kk_next, j, 8);
+        if (sub == 0) issue(j, min(n0 + 8 + j, n_end - 1), k);
+      }
+    }
+    phase ^= 1u;
+    // transpose-reduce: after the three rounds lane `sub` holds the total of pair `sub`
+    float r4[4], r2[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = (sub & 4) ? part[j] : part[j + 4];
+      const float keep = (sub & 4) ? part[j + 4] : part[j];
+      r4[j] = keep + __shfl_xor_sync(gmask, send, 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = (sub & 2) ? r4[j] : r4[j + 2];
+      const float keep = (sub & 2) ? r4[j + 2] : r4[j];
+      r2[j] = keep + __shfl_xor_sync(gmask, send, 2);
+    }
+    const float send = (sub & 1) ? r2[0] : r2[1];
+    const float keep = (sub & 1) ? r2[1] : r2[0];
+    const float frame = keep + __shfl_xor_sync(gmask, send, 1);
+    const int nj = n0 + sub;
+    if (live_m && nj < n_end) {
+      const int64_t oj = (int64_t)mm * ld + nj;
+      if (out_frame) out_frame[oj] = frame;
+      if (fused) {
+        const float v = fuse_branch(clip[oj], frame, wc, wf, wb);
+        fused[oj] = accumulate ? __fadd_rn(fused[oj], v) : v;
+      }
+    }
+  }
+}
+
+#endif  // DKD_FF_BULK
+
 // CSR flavour (exact rescoring of candidates): one 8-lane group per CSR entry.
-__global__ void __launch_bounds__(256)
+// kD > 0: the row length is a compile-time constant and the body is fully unrolled (query row + table row: 2 x kD / 32
+// float4 per lane) — the kernel is a latency-bound random gather of 1.5 KB rows from HBM / L2, so the loads in flight
+// per SM set its speed; the summation order is that of the generic loop (bit-identical results).
+// Round-2 A/B (whole step, two launches, ms): generic loop at 40 registers 0.75; the fully unrolled D = 384 body at
+// 3 / 4 / 5 blocks per SM 0.79 / 0.67 / 0.65; forcing all 24 loads ahead of the arithmetic (116 registers, 2 blocks) 0.96.
+#ifndef DKD_CSR_MINBLOCKS
+#define DKD_CSR_MINBLOCKS 5    // 0: plain __launch_bounds__(256) and the generic loop (round-1 kernel)
+#endif
+#if DKD_CSR_MINBLOCKS > 0
+#define DKD_CSR_BOUNDS __launch_bounds__(256, DKD_CSR_MINBLOCKS)
+#else
+#define DKD_CSR_BOUNDS __launch_bounds__(256)
+#endif
+template <int kD>
+__global__ void DKD_CSR_BOUNDS
 frame_fuse_csr_kernel(const float* __restrict__ q, const float* __restrict__ table,
                       const float* __restrict__ clip, const int32_t* __restrict__ key_clip,
                       const int32_t* __restrict__ vid_ptr, const int32_t* __restrict__ q_list,
@@ -312,7 +476,27 @@ frame_fuse_csr_kernel(const float* __restrict__ q, const float* __restrict__ tab
       if (dense_ld > 0) ce = (int64_t)q_list[e] * dense_ld + n;
       int k = key_clip[ce];
       k = k < 0 ? 0 : (k >= P ? P - 1 : k);
-      acc = RowLoader<float>::dot(q + (int64_t)q_list[e] * D, table + ((int64_t)n * P + k) * D, D, sub);
+      const float* a = q + (int64_t)q_list[e] * D;
+      const float* b = table + ((int64_t)n * P + k) * D;
+      if (kD > 0) {
+        constexpr int kN = kD > 0 ? kD / 32 : 1;
+        float4 x[kN], y[kN];
+#pragma unroll
+        for (int i = 0; i < kN; ++i) {
+          x[i] = __ldg(reinterpret_cast<const float4*>(a + sub * 4 + 32 * i));
+          y[i] = __ldg(reinterpret_cast<const float4*>(b + sub * 4 + 32 * i));
+        }
+#ifdef DKD_CSR_BARRIER
+        asm volatile("" ::: "memory");                    // keep every load of the entry ahead of the arithmetic
+#endif
+#pragma unroll
+        for (int i = 0; i < kN; ++i) {
+          acc = fmaf(x[i].x, y[i].x, acc); acc = fmaf(x[i].y, y[i].y, acc);
+          acc = fmaf(x[i].z, y[i].z, acc); acc = fmaf(x[i].w, y[i].w, acc);
+        }
+      } else {
+        acc = RowLoader<float>::dot(a, b, D, sub);
+      }
     }
 #pragma unroll
     for (int s = 4; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
@@ -392,6 +576,18 @@ extern "C" int dkd_frame_fuse(const void* q, const void* table, int32_t is_f16, 
     dim3 gh((M + 31) / 32, (Nv + vchunk - 1) / vchunk);
     const __half* qh = (const __half*)q;
     const __half* th = (const __half*)table;
+#if DKD_FF_BULK
+    if (D == 384) {   // bulk-copy ring (see frame_fuse_h_bulk_kernel); other widths keep the register version
+      const int vch = 64;
+      dim3 gb((M + 31) / 32, (Nv + vch - 1) / vch);
+      const size_t smem = (size_t)32 * 8 * 768 + 32 * 8 * sizeof(uint64_t);
+      DKD_CUDA_TRY(cudaFuncSetAttribute(frame_fuse_h_bulk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      frame_fuse_h_bulk_kernel<6><<<gb, 256, smem, st>>>(qh, th, clip_scores, key_clip, M, Nv, P, ld, w_clip, w_frame,
+                                                         w_branch, accumulate, vch, out_frame, fused);
+      DKD_LAUNCH_CHECK();
+      return DKD_OK;
+    }
+#endif
 #define DKD_FF_H(C)                                                                                              \
   frame_fuse_h_kernel<C><<<gh, 256, 0, st>>>(qh, th, clip_scores, key_clip, M, Nv, P, ld, w_clip, w_frame,       \
                                              w_branch, accumulate, vchunk, out_frame, fused)
@@ -427,9 +623,14 @@ extern "C" int dkd_frame_fuse_csr(const float* q, const float* table, const floa
   if (D <= 0 || D % 32 != 0 || P <= 0) return DKD_ERR_SHAPE;
   if (Nv == 0) return DKD_OK;
   dim3 grid(Nv, 4);
-  frame_fuse_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, table, clip_scores, key_clip, vid_ptr,
-                                                                q_list, slot, Nv, P, D, w_clip, w_frame,
-                                                                w_branch, accumulate, cand_scores, dense_ld);
+  if (D == 384 && DKD_CSR_MINBLOCKS > 0)
+    frame_fuse_csr_kernel<384><<<grid, 256, 0, (cudaStream_t)stream>>>(q, table, clip_scores, key_clip, vid_ptr, q_list,
+                                                                       slot, Nv, P, D, w_clip, w_frame, w_branch,
+                                                                       accumulate, cand_scores, dense_ld);
+  else
+    frame_fuse_csr_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(q, table, clip_scores, key_clip, vid_ptr, q_list,
+                                                                     slot, Nv, P, D, w_clip, w_frame, w_branch,
+                                                                     accumulate, cand_scores, dense_ld);
   DKD_LAUNCH_CHECK();
   return DKD_OK;
 }

@@ -592,6 +592,8 @@ def main():
     _lib.set_timed({gemm_entry})
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
+    engine.finish()
+    fallbacks_before = engine.STATS["certify_fallback_queries"]
     ev[0].record()
     for _ in range(args.steps):
         top_s, top_i = step(qs)
@@ -599,7 +601,8 @@ def main():
     barrier()
     # deferred certificates of the timed steps: a fallback (never observed at these shapes) would have been applied
     # AFTER the timed region, so in that case the steps are timed again with the certificate read back inside each step
-    if any_rank(engine.finish()) and not stream:
+    engine.finish()
+    if any_rank(engine.STATS["certify_fallback_queries"] > fallbacks_before) and not stream:
         cert_mode[0] = True
         _lib.set_timed({gemm_entry})
         barrier()
@@ -609,7 +612,7 @@ def main():
         ev[1].record()
         barrier()
     clocks = sampler.result()
-    timed_fallbacks = engine.STATS["certify_fallback_queries"]      # of warm-up + timed steps (0: nothing was re-ranked)
+    timed_fallbacks = engine.STATS["certify_fallback_queries"] - fallbacks_before   # 0: nothing was re-ranked
     ms_total = ev[0].elapsed_time(ev[1])
     gemm_ms = _lib.timed_results().get(gemm_entry, [])
     _lib.set_timed(set())
@@ -645,10 +648,14 @@ def main():
 
     copy_stream = torch.cuda.Stream(dev)
 
+    e2e_fb = [0]
+
     def run_e2e(n_steps):
         """n_steps passes, each fed from pinned host memory and drained to pinned host memory.  The copies of
         step i+1 (H2D) and step i-1 (D2H) run on a copy stream under the kernels of step i."""
         main = torch.cuda.current_stream()
+        engine.finish()
+        e2e_fb[0] = engine.STATS["certify_fallback_queries"]
 
         def upload():
             with torch.cuda.stream(copy_stream):
@@ -678,7 +685,8 @@ def main():
         # the steps' certificates are looked at once here (no host synchronisation inside the loop); a fallback would
         # have patched lists that were already copied out, so in that case the leg is timed again with the certificate
         # read back inside every step
-        if engine.finish():
+        engine.finish()
+        if engine.STATS["certify_fallback_queries"] > e2e_fb[0]:
             cert_mode[0] = True
 
     run_e2e(1 if stream else 2)
@@ -731,13 +739,16 @@ def main():
             step(qs, precision="shortcut")
         barrier()
         vsteps = max(3, args.steps // 4)
+        engine.finish()
+        v_fb = engine.STATS["certify_fallback_queries"]
         ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev3[0].record()
         for _ in range(vsteps):
             v_s, v_i = step(qs, precision="shortcut")
         ev3[1].record()
         barrier()
-        if any_rank(engine.finish()):       # a deferred certificate failed somewhere: lists for the comparison below
+        engine.finish()
+        if any_rank(engine.STATS["certify_fallback_queries"] > v_fb):   # a deferred certificate failed somewhere
             v_s, v_i = step(qs, precision="shortcut", cert=True)
         v_ms = ev3[0].elapsed_time(ev3[1]) / vsteps
         if world > 1:
@@ -857,13 +868,16 @@ def main():
             step(qs, corpus=pc_s)
         barrier()
         ssteps = max(3, args.steps // 4)
+        engine.finish()
+        s_fb = engine.STATS["certify_fallback_queries"]
         ev4 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev4[0].record()
         for _ in range(ssteps):
             st_s, st_i = step(qs, corpus=pc_s)
         ev4[1].record()
         barrier()
-        strong_fallbacks = engine.finish()        # local: patches this rank's lists in place if a certificate failed
+        engine.finish()                           # local: patches this rank's lists in place if a certificate failed
+        strong_fallbacks = engine.STATS["certify_fallback_queries"] - s_fb
         if any_rank(strong_fallbacks):            # ... after they were merged: redo one step with the in-step read-back
             st_s, st_i = step(qs, corpus=pc_s, cert=True)
         s_ms = ev4[0].elapsed_time(ev4[1]) / ssteps

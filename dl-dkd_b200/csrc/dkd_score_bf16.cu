@@ -45,8 +45,10 @@ struct Top2 {
 };
 constexpr float kNegHuge = -3.0e38f;
 
-// one 16-column chunk: r[0..15] raw fp32 bits, chunk id `cid`
-template <bool kHasMask>
+// one 16-column chunk: r[0..15] raw fp32 bits, chunk id `cid`.  kTop2 = false (no gap / flag output requested: the frame
+// head) tracks the maximum only: LOP3 + FMNMX per element instead of LOP3 + 3 FMNMX — the epilogue, not the tensor
+// pipe, bounds the R = 128 problem.
+template <bool kHasMask, bool kTop2>
 __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, const uint8_t* mrow) {
   const float before = t.best;
 #pragma unroll
@@ -56,7 +58,7 @@ __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, 
       if (__ldg(mrow + j) == 0) b = __float_as_uint(DKD_MASKED_SCORE);
     }
     const float u = __uint_as_float((b & 0xfffffff0u) | (uint32_t)(15 - j));
-    t.second = fmaxf(t.second, fminf(t.best, u));
+    if (kTop2) t.second = fmaxf(t.second, fminf(t.best, u));
     t.best = fmaxf(t.best, u);
   }
   if (t.best != before) t.chunk = cid;
@@ -102,7 +104,7 @@ struct __align__(8) SmemCtl {
 // hold different query tiles and each half of the corpus tile; the leader (rank 0) issues M=256 MMAs
 // that read both halves, which halves the shared-memory operand traffic and the L2->SM corpus traffic
 // per CTA and doubles the depth of the corpus ring.
-template <bool kHasMask, int kCta>
+template <bool kHasMask, int kCta, bool kTop2>
 __global__ void __launch_bounds__(kNumThreads, 1)
 score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                       const GemmParams p) {
@@ -312,7 +314,7 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const int c = c_lo + i;
-            if (c < c_hi) top2_chunk<kHasMask>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
+            if (c < c_hi) top2_chunk<kHasMask, kTop2>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
           }
           tc_fence_before();
           __syncwarp();
@@ -414,10 +416,10 @@ static int pick_block_n(int R) {
 
 using namespace dkd;
 
-template <bool kHasMask, int kCta>
+template <bool kHasMask, int kCta, bool kTop2>
 static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const GemmParams& p, int grid,
                        size_t smem_bytes, cudaStream_t st) {
-  auto kern = score_max_bf16_kernel<kHasMask, kCta>;
+  auto kern = score_max_bf16_kernel<kHasMask, kCta, kTop2>;
   DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -495,10 +497,17 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   const int grid = (int)(num_items < workers ? num_items : workers) * cta;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (cta == 2) return mask ? launch_gemm<true, 2>(map_q, map_x, p, grid, smem_bytes, st)
-                            : launch_gemm<false, 2>(map_q, map_x, p, grid, smem_bytes, st);
-  return mask ? launch_gemm<true, 1>(map_q, map_x, p, grid, smem_bytes, st)
-              : launch_gemm<false, 1>(map_q, map_x, p, grid, smem_bytes, st);
+  const bool top2 = out_gap || out_flags || flag_list;      // the runner-up is tracked only when somebody reads it
+  if (top2) {
+    if (cta == 2) return mask ? launch_gemm<true, 2, true>(map_q, map_x, p, grid, smem_bytes, st)
+                              : launch_gemm<false, 2, true>(map_q, map_x, p, grid, smem_bytes, st);
+    return mask ? launch_gemm<true, 1, true>(map_q, map_x, p, grid, smem_bytes, st)
+                : launch_gemm<false, 1, true>(map_q, map_x, p, grid, smem_bytes, st);
+  }
+  if (cta == 2) return mask ? launch_gemm<true, 2, false>(map_q, map_x, p, grid, smem_bytes, st)
+                            : launch_gemm<false, 2, false>(map_q, map_x, p, grid, smem_bytes, st);
+  return mask ? launch_gemm<true, 1, false>(map_q, map_x, p, grid, smem_bytes, st)
+              : launch_gemm<false, 1, false>(map_q, map_x, p, grid, smem_bytes, st);
 }
 
 extern "C" int dkd_score_max_bf16(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const uint16_t* x_bf16,

@@ -287,6 +287,16 @@ def finish(keep_last=0):
     return n
 
 
+def poll():
+    """Resolve, without blocking, the deferred certificates whose outcome has already reached the host (oldest first).
+    rank() calls this on entry, so a stream of deferred calls keeps at most the last few outcomes — and the buffers
+    they reference — alive; without it every call would have to allocate fresh device memory."""
+    n = 0
+    while PENDING and PENDING[0].event.query():
+        n += PENDING.pop(0).resolve()
+    return n
+
+
 def _apply_fallback(pc, pq, unsure, n_unsure, out_s, out_i, args):
     STATS["certify_checked_queries"] += pq.M
     STATS["certify_fallback_queries"] += n_unsure
@@ -319,6 +329,8 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     """
     nb = len(pc.branches)
     wbs = _branch_weights(nb)
+    if PENDING:
+        poll()
     if pq.M == 0 or pc.Nv == 0:  # no queries / empty shard: K columns of padding (score -inf, id -1), like dkd_topk
         dev = pc.mask_u8.device
         out = (torch.full((pq.M, K), float("-inf"), dtype=torch.float32, device=dev),

@@ -8,7 +8,8 @@ Same names, arguments and return values as the reference:
 
 Extra `opt` fields (all optional; defaults reproduce the reference):
     scoring    "frame" (default: the head the reference ships) | "two_scale" (north_star head)
-    precision  "exact" (default: fp32 kernels) | "bf16" (tcgen05 GEMM, scores within 1e-3)
+    precision  "exact" (default: fp32 kernels) | "bf16" (tcgen05 GEMM, scores within 1e-3) | "fp16" | "shortcut"
+    ambiguity_tau, candidates   the two empirical constants of the approximate pass (engine.AMBIGUITY_TAU, 128)
 Extra entry point: rank_queries(...) -> per-query top-K on the device (the benchmarked hot path).
 """
 import logging
@@ -195,7 +196,8 @@ def rank_queries(model, eval_dataset, opt, ctx_info, K=100, return_dense=False):
     for lo in range(0, qs[0].shape[0], chunk):
         pq = engine.prepare_queries([q[lo: lo + chunk] for q in qs], want_bf16=precision == "bf16")
         outs.append(engine.rank(pc, pq, K=K, head=scoring, precision=precision, w_clip=model.clip_scale_w,
-                                w_frame=model.frame_scale_w, certify="deferred", return_dense=return_dense))
+                                w_frame=model.frame_scale_w, certify="deferred", return_dense=return_dense,
+                                tau=_opt(opt, "ambiguity_tau", None), Kc=int(_opt(opt, "candidates", 128))))
     engine.finish()
     res = tuple(torch.cat([o[j] for o in outs]) for j in range(len(outs[0])))
     return res[:2] + (metas,) + res[2:]

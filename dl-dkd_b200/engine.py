@@ -324,8 +324,8 @@ def rank(pc: PreparedCorpus, pq: PreparedQueries, K=100, head="two_scale", preci
     to precision="exact" for every query instead of "for every query we tested".
       certify=True        the check is read back immediately (one scalar device->host read per call);
       certify="deferred"  no host synchronisation: the outcome is queued in PENDING and engine.finish() — called by
-                          the consumer before it reads the lists — applies the (rare) exact re-rank in place.  This
-                          form can be captured in a CUDA graph.
+                          the consumer before it reads the lists — applies the (rare) exact re-rank in place; outcomes
+                          that have already reached the host are resolved on the next rank() entry (engine.poll()).
     """
     nb = len(pc.branches)
     wbs = _branch_weights(nb)

@@ -960,6 +960,13 @@ def main():
                     "flops_per_launch": flops_launch, "launches_timed": len(gemm_ms), "avg_launch_ms": gemm_avg_ms,
                     "share_of_step": (n_launch_step * gemm_avg_ms / ms_step) if gemm_avg_ms else None,
                     "traffic": traffic}
+        # the WHOLE step against the same roofline (north_star's target; SURVEY.md §8d counts the contraction's
+        # algorithmic flops only and quotes the target on the sustained peak: the step is a long back-to-back loop)
+        step_flops = flops_launch * n_launch_step                      # per GPU: every rank scores its own shard
+        step_tf = step_flops / (ms_step * 1e-3) / 1e12
+        roofline["step"] = {"algorithmic_flops_per_gpu": step_flops, "achieved": step_tf, "unit": "TFLOP/s per GPU",
+                            "frac_of_burst_peak": step_tf / pk["bf16_burst"],
+                            "frac_of_sustained_peak": step_tf / pk["bf16_sustained"]}
         line = {"metric": "query-video pairs scored+ranked/sec", "value": value, "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

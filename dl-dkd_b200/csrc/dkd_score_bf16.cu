@@ -22,6 +22,7 @@
 //
 // Operand layout: K-major, 128-byte swizzle (TMA SWIZZLE_128B <-> UMMA SWIZZLE_128B descriptors),
 // one K block = 64 bf16 = 128 B per row, 8-row groups 1024 B apart.
+#include <cstddef>
 #include "dkd_umma.cuh"
 
 namespace dkd {
@@ -32,7 +33,6 @@ constexpr int kUmmaK = 16;
 constexpr int kMaxKBlocks = 8;    // D <= 512
 constexpr int kMaxStages = 12;
 constexpr int kNumThreads = 384;
-constexpr int kNumEpiThreads = 256;
 // Warp roles.  The issue scheduler favours higher warp ids within an SM sub-partition, so the three
 // latency-critical single-lane roles sit above the eight ALU-heavy epilogue warps (0..7).
 constexpr int kWarpB = 8, kWarpMma = 9, kWarpA = 10;
@@ -51,15 +51,34 @@ constexpr float kNegHuge = -3.0e38f;
 template <bool kHasMask, bool kTop2>
 __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, const uint8_t* mrow) {
   const float before = t.best;
+  // The mask depends on (video, column) only, so it is uniform over the warp (lanes are query rows): one 16-byte
+  // load per chunk and a divergence-free branch.  Chunks without a masked column (every chunk of a full-length
+  // video) take the unmasked instruction stream; rows are 16-byte aligned because R % 16 == 0.
+  bool any_masked = false;
+  uint4 mw = make_uint4(0, 0, 0, 0);
+  if (kHasMask) {
+    mw = __ldg(reinterpret_cast<const uint4*>(mrow));
+    const uint32_t z = ((mw.x - 0x01010101u) & ~mw.x) | ((mw.y - 0x01010101u) & ~mw.y) |
+                       ((mw.z - 0x01010101u) & ~mw.z) | ((mw.w - 0x01010101u) & ~mw.w);
+    any_masked = (z & 0x80808080u) != 0;          // some byte of the 16 is zero
+  }
+  if (kHasMask && any_masked) {
+    const uint32_t w[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    uint32_t b = r[j];
-    if (kHasMask) {
-      if (__ldg(mrow + j) == 0) b = __float_as_uint(DKD_MASKED_SCORE);
+    for (int j = 0; j < 16; ++j) {
+      uint32_t b = r[j];
+      if (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) == 0) b = __float_as_uint(DKD_MASKED_SCORE);
+      const float u = __uint_as_float((b & 0xfffffff0u) | (uint32_t)(15 - j));
+      if (kTop2) t.second = fmaxf(t.second, fminf(t.best, u));
+      t.best = fmaxf(t.best, u);
     }
-    const float u = __uint_as_float((b & 0xfffffff0u) | (uint32_t)(15 - j));
-    if (kTop2) t.second = fmaxf(t.second, fminf(t.best, u));
-    t.best = fmaxf(t.best, u);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float u = __uint_as_float((r[j] & 0xfffffff0u) | (uint32_t)(15 - j));
+      if (kTop2) t.second = fmaxf(t.second, fminf(t.best, u));
+      t.best = fmaxf(t.best, u);
+    }
   }
   if (t.best != before) t.chunk = cid;
 }
@@ -88,23 +107,56 @@ struct GemmParams {
   int64_t flag_cap;
   int f16;            // operands are IEEE half instead of bf16 (same 2-byte layout, same MMA kind::f16 rate)
   int64_t ld_out;
+  int nv_real;        // kPair kernels: Nv counts video PAIRS and R = 2 x rows per video; nv_real = videos
 };
 
 struct __align__(8) SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  // One full / empty pair for the whole resident query tile.  Handing the tile over per K block (slab k of the next
+  // item loaded while the last corpus tile still multiplies slabs k+1..) was measured SLOWER (same box, round 2: two-scale
+  // GEMM 6.41 -> 6.75 ms, frame head 1.79 -> 1.83 ms): the extra waits / commits sit on the single issuing thread.
   uint64_t a_full, a_empty;
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  // keep these two LAST: kPair kernels do not allocate them (host: offsetof(SmemCtl, xchg))
   float2 xchg[2][128];  // half-1 -> half-0 epilogue exchange (best, second), double buffered
   int xchg_chunk[2][128];
 };
+
+// Final value of one (query m, video v): best / runner-up carry the column position in their 4 low mantissa bits.
+__device__ __forceinline__ void emit_result(const GemmParams& p, int m, int v, float b, float s2, int ch) {
+  const uint32_t bb = __float_as_uint(b);
+  const int idx = (ch << 4) + 15 - (int)(bb & 15u);
+  float val = __uint_as_float((bb & 0xfffffff0u) | 8u);
+  float sec = __uint_as_float((__float_as_uint(s2) & 0xfffffff0u) | 8u);
+  const bool dead = val < -0.99e10f;             // fully masked video: exactly the fill value, first index (torch.max)
+  if (dead) val = DKD_MASKED_SCORE;
+  const int64_t o64 = (int64_t)m * p.ld_out + v;
+  p.out_max[o64] = val;
+  if (p.out_arg) p.out_arg[o64] = dead ? 0 : idx;
+  const float gap = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
+  if (p.out_gap) p.out_gap[o64] = gap;
+  if (gap < p.tau) {
+    if (p.out_flags) atomicOr(&p.out_flags[(int64_t)m * p.flag_words + (v >> 5)], 1u << (v & 31));
+    if (p.flag_list) {
+      const int pos = atomicAdd(&p.flag_cnt[v], 1);
+      if (pos < p.flag_cap) p.flag_list[(int64_t)v * p.flag_cap + pos] = m;
+    }
+  }
+}
 
 // kCta = 1: one CTA per tile (cta_group::1).  kCta = 2: CTA pair (cluster of 2, cta_group::2): the two CTAs
 // hold different query tiles and each half of the corpus tile; the leader (rank 0) issues M=256 MMAs
 // that read both halves, which halves the shared-memory operand traffic and the L2->SM corpus traffic
 // per CTA and doubles the depth of the corpus ring.
-template <bool kHasMask, int kCta, bool kTop2>
+//
+// kPair (CTA pairs only; short videos, R <= 128 — the frame head): one MMA tile spans TWO videos (N = 2 R <= 256), CTA
+// r of the pair stages video 2 v + r.  The tile's two column halves already belong to the two epilogue warps of every
+// TMEM lane quarter, so each warp owns one whole video: no exchange of the halves through shared memory, half the
+// accumulator handshakes and half the MMA instructions per video (the R = 128 problem is bound by that per-tile
+// overhead, not by the tensor pipe).  The host passes Nv = number of pairs, R = block_n = 2 x rows per video.
+template <bool kHasMask, int kCta, bool kTop2, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                       const GemmParams p) {
@@ -163,7 +215,9 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int v1 = min(v0 + p.video_chunk, p.Nv);
         for (int v = v0; v < v1; ++v) {
           for (int t = 0; t < tiles_per_video; ++t) {
-            const int row = v * p.R + t * p.block_n;
+            int row = v * p.R + t * p.block_n;
+            // odd number of videos: the second half of the last pair stages the last video again (result unused)
+            if (kPair && cta_rank == 1 && 2 * v + 1 >= p.nv_real) row -= b_rows;
             for (int kb = 0; kb < num_kb; kb += kbs) {
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               uint8_t* dst = smem_b + (size_t)stage * b_stage_bytes;
@@ -290,6 +344,44 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const int v0 = vchunk * p.video_chunk;
       const int v1 = min(v0 + p.video_chunk, p.Nv);
       const int m = q_tile * kBlockM + row_in_tile;
+      if constexpr (kPair) {
+        // one whole video per warp: column half `half` of pair v is video 2 v + half
+        const int rr = p.R >> 1;                    // rows per video
+        const int nch = rr >> 4;                    // 16-column chunks per video (<= 8)
+        for (int v = v0; v < v1; ++v, ++tile_ctr) {
+          const int vr = 2 * v + half;
+          Top2 t2;
+          t2.best = kNegHuge; t2.second = kNegHuge; t2.chunk = 0;
+          const uint8_t* mvid = kHasMask ? p.mask + (int64_t)min(vr, p.nv_real - 1) * rr : nullptr;
+          const uint32_t as = tile_ctr & 1u;
+          const uint32_t aphase = (tile_ctr >> 1) & 1u;
+          mbar_wait(&ctl->tmem_full[as], aphase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)p.block_n +
+                                 (uint32_t)(half * rr);
+          // two rounds of <= 4 chunks: 64 accumulator registers in flight instead of 128
+#pragma unroll 1
+          for (int c0 = 0; c0 < nch; c0 += 4) {
+            uint32_t r[64];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int c = c0 + 2 * i;
+              if (c + 1 < nch) tmem_ld32_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+              else if (c < nch) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c0 + i;
+              if (c < nch) top2_chunk<kHasMask, kTop2>(t2, r + 16 * i, c, kHasMask ? mvid + (c << 4) : nullptr);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
+          if (vr < p.nv_real && m < p.M) emit_result(p, m, vr, t2.best, t2.second, t2.chunk);
+        }
+      } else {
       for (int v = v0; v < v1; ++v, ++vctr) {
         Top2 t2;
         t2.best = kNegHuge; t2.second = kNegHuge; t2.chunk = 0;
@@ -339,27 +431,10 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           const bool take = (o.x > b) || (o.x == b && oc < ch);
           s2 = fmaxf(fmaxf(s2, o.y), take ? b : o.x);
           if (take) { b = o.x; ch = oc; }
-          if (m < p.M) {
-            const uint32_t bb = __float_as_uint(b);
-            const int idx = (ch << 4) + 15 - (int)(bb & 15u);
-            float val = __uint_as_float((bb & 0xfffffff0u) | 8u);
-            float sec = __uint_as_float((__float_as_uint(s2) & 0xfffffff0u) | 8u);
-            if (val < -0.99e10f) val = DKD_MASKED_SCORE;   // fully masked video: exactly the fill value
-            const int64_t o64 = (int64_t)m * p.ld_out + v;
-            p.out_max[o64] = val;
-            if (p.out_arg) p.out_arg[o64] = idx;
-            const float gap = (s2 <= kNegHuge) ? 3.0e38f : val - sec;
-            if (p.out_gap) p.out_gap[o64] = gap;
-            if (gap < p.tau) {
-              if (p.out_flags) atomicOr(&p.out_flags[(int64_t)m * p.flag_words + (v >> 5)], 1u << (v & 31));
-              if (p.flag_list) {
-                const int pos = atomicAdd(&p.flag_cnt[v], 1);
-                if (pos < p.flag_cap) p.flag_list[(int64_t)v * p.flag_cap + pos] = m;
-              }
-            }
-          }
+          if (m < p.M) emit_result(p, m, v, b, s2, ch);
         }
       }
+      }  // !kPair
     }
   }
 
@@ -416,10 +491,10 @@ static int pick_block_n(int R) {
 
 using namespace dkd;
 
-template <bool kHasMask, int kCta, bool kTop2>
+template <bool kHasMask, int kCta, bool kTop2, bool kPair = false>
 static int launch_gemm(const CUtensorMap& map_q, const CUtensorMap& map_x, const GemmParams& p, int grid,
                        size_t smem_bytes, cudaStream_t st) {
-  auto kern = score_max_bf16_kernel<kHasMask, kCta, kTop2>;
+  auto kern = score_max_bf16_kernel<kHasMask, kCta, kTop2, kPair>;
   DKD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -449,13 +524,21 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   if ((reinterpret_cast<uintptr_t>(q_bf16) & 15) || (reinterpret_cast<uintptr_t>(x_bf16) & 15)) return DKD_ERR_ALIGN;
   if (M == 0 || Nv == 0) return DKD_OK;
   if ((int64_t)Nv * R > 0x7fffffffLL) return DKD_ERR_SHAPE;
-  const int block_n = pick_block_n(R);
-  if (block_n == 0) return DKD_ERR_SHAPE;
+  if (mask && (reinterpret_cast<uintptr_t>(mask) & 15)) return DKD_ERR_ALIGN;   // 16-byte mask loads per chunk
 
   int dev = 0, sms = 0, max_smem = 0;
   DKD_CUDA_TRY(cudaGetDevice(&dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DKD_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+  // Short videos (R <= 128: the frame head) on CTA pairs: one N = 2 R tile spans two videos (kPair kernels).
+#ifdef DKD_NO_PAIR_TILES     // A/B builds only (tools/build_variant.sh)
+  const bool pair = false;
+#else
+  const bool pair = R <= 128 && Nv >= 2 && Mpad % (2 * kBlockM) == 0 && sms >= 2;
+#endif
+  const int block_n = pair ? 2 * R : pick_block_n(R);
+  if (block_n == 0) return DKD_ERR_SHAPE;
 
   // CTA pairs (cta_group::2) whenever the shapes allow: two query tiles per pair, corpus tile split in
   // halves of a multiple of 8 rows.
@@ -465,11 +548,17 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   const size_t a_bytes = (size_t)num_kb * kBlockM * kBlockK * 2;
   // K blocks per ring stage.  Every stage costs one full/empty handshake on the single issuing thread,
   // which is the scarce resource: CTA pairs (half-size stages) take 3 K blocks per stage when D allows,
-  // measured 1.38 PF vs 1.05 PF with 1 (profiles/r1_gemm_variants.md).
+  // measured 1.38 PF vs 1.05 PF with 1 (profiles/r1_gemm_variants.md).  Pair tiles stage R <= 128 rows per CTA and
+  // issue N <= 256 instructions (twice the tensor time per handshake): 2 K blocks per stage keep >= 4 stages.
   int kbs = 1;
-  if (cta == 2) kbs = (num_kb % 3 == 0) ? 3 : ((num_kb % 2 == 0) ? 2 : 1);
+  if (cta == 2) kbs = (num_kb % 3 == 0 && !(pair && R > 88)) ? 3 : ((num_kb % 2 == 0) ? 2 : 1);
+#ifdef DKD_PAIR_KBS          // A/B builds only
+  if (pair && num_kb % DKD_PAIR_KBS == 0) kbs = DKD_PAIR_KBS;
+#endif
   const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2 * kbs;
-  const size_t fixed = a_bytes + sizeof(SmemCtl) + 1024 /* alignment slack */ + 256;
+  // pair tiles never exchange column halves: without the exchange buffers (the tail of SmemCtl) a fourth 32 KB stage fits
+  const size_t ctl_bytes = pair ? offsetof(SmemCtl, xchg) : sizeof(SmemCtl);
+  const size_t fixed = a_bytes + ctl_bytes + 1024 /* alignment slack */ + 256;
   if ((size_t)max_smem < fixed + 2 * b_stage) return DKD_ERR_SHAPE;
   int stages = (int)(((size_t)max_smem - fixed) / b_stage);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -482,22 +571,31 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   if (rc) return rc;
 
   GemmParams p{};
-  p.M = M; p.Mpad = Mpad; p.Nv = Nv; p.R = R; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
+  p.M = M; p.Mpad = Mpad; p.D = D; p.block_n = block_n; p.stages = stages; p.kb_per_stage = kbs;
+  p.nv_real = Nv;
+  const int nv_items = pair ? (Nv + 1) / 2 : Nv;     // scheduling unit: a video, or a pair of videos
+  p.Nv = nv_items; p.R = pair ? 2 * R : R;
   p.f16 = f16 ? 1 : 0;
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
   p.flag_cnt = flag_cnt; p.flag_list = flag_list; p.flag_cap = flag_cap;
-  // videos per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
+  // videos (pairs) per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
   const int num_q_tiles = Mpad / (kBlockM * cta);
   const int workers = sms / cta;
   int vc = 16;
-  while (vc > 1 && (int64_t)num_q_tiles * ((Nv + vc - 1) / vc) < (int64_t)workers * 8) vc >>= 1;
+  while (vc > 1 && (int64_t)num_q_tiles * ((nv_items + vc - 1) / vc) < (int64_t)workers * 8) vc >>= 1;
   p.video_chunk = vc;
-  const int64_t num_items = (int64_t)num_q_tiles * ((Nv + vc - 1) / vc);
+  const int64_t num_items = (int64_t)num_q_tiles * ((nv_items + vc - 1) / vc);
   const int grid = (int)(num_items < workers ? num_items : workers) * cta;
 
   cudaStream_t st = (cudaStream_t)stream;
   const bool top2 = out_gap || out_flags || flag_list;      // the runner-up is tracked only when somebody reads it
+  if (pair) {   // pair == true implies cta == 2 (R % 16 == 0)
+    if (top2) return mask ? launch_gemm<true, 2, true, true>(map_q, map_x, p, grid, smem_bytes, st)
+                          : launch_gemm<false, 2, true, true>(map_q, map_x, p, grid, smem_bytes, st);
+    return mask ? launch_gemm<true, 2, false, true>(map_q, map_x, p, grid, smem_bytes, st)
+                : launch_gemm<false, 2, false, true>(map_q, map_x, p, grid, smem_bytes, st);
+  }
   if (top2) {
     if (cta == 2) return mask ? launch_gemm<true, 2, true>(map_q, map_x, p, grid, smem_bytes, st)
                               : launch_gemm<false, 2, true>(map_q, map_x, p, grid, smem_bytes, st);

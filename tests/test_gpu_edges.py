@@ -56,6 +56,11 @@ def test_single_frame_and_fully_padded_videos(ops):
     (s, a), = engine.score_frame_head(pc, pq, "exact")
     assert (s.cpu() - ref).abs().max() <= 2e-6
     assert bool((s[:, 7] == -1e10).all()) and bool((a[:, 3] == 0).all())
+    # the tcgen05 GEMM (pair tiles: video 7 is the second half of pair 3): same fill value, first argmax
+    (sb, ab), = engine.score_frame_head(pc, pq, "bf16")
+    assert bool((sb[:, 7] == -1e10).all()) and bool((ab[:, 7] == 0).all()) and bool((ab[:, 3] == 0).all())
+    live = [n for n in range(12) if n != 7]
+    assert (sb.cpu() - ref)[:, live].abs().max() <= 1e-3
     _, ids = engine.rank(pc, pq, K=12, head="frame", precision="bf16")
     assert bool((ids[:, -1] == 7).all())
 

@@ -207,6 +207,12 @@ def test_clip_score_f32_csr_and_scatter(ops):
     (300, 128, 150, 528, 384, False),  # three query tiles -> single-CTA kernel
     (700, 256, 61, 128, 384, True),    # CTA pair with mask, three tile pairs
     (10, 128, 4, 64, 128, True),
+    # pair tiles (R <= 128 on CTA pairs: one N = 2 R tile spans two videos, dkd_score_bf16.cu kPair)
+    (300, 256, 45, 112, 384, True),    # 7 chunks per video (16-column tail load), odd video count
+    (513, 256, 128, 128, 384, False),  # unmasked, three tile pairs, even video count
+    (100, 256, 7, 48, 128, True),      # 3 chunks per video, D = 128
+    (256, 256, 2, 16, 192, True),      # smallest: one pair, one chunk per video; 3 K blocks
+    (256, 256, 3, 32, 128, False),     # odd count without mask: the last pair's second half is a repeat
 ])
 def test_score_max_bf16(ops, M, pad, Nv, R, D, masked):
     g = torch.Generator().manual_seed(77)

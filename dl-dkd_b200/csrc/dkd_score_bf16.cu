@@ -555,6 +555,9 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
 #ifdef DKD_PAIR_KBS          // A/B builds only
   if (pair && num_kb % DKD_PAIR_KBS == 0) kbs = DKD_PAIR_KBS;
 #endif
+#ifdef DKD_MAIN_KBS          // A/B builds only (2 K blocks per stage at N = 176: 6.5 -> 7.1 ms, profiles/r2_ab_gemm_items.md)
+  if (!pair && cta == 2 && num_kb % DKD_MAIN_KBS == 0) kbs = DKD_MAIN_KBS;
+#endif
   const size_t b_stage = (size_t)(block_n / cta) * kBlockK * 2 * kbs;
   // pair tiles never exchange column halves: without the exchange buffers (the tail of SmemCtl) a fourth 32 KB stage fits
   const size_t ctl_bytes = pair ? offsetof(SmemCtl, xchg) : sizeof(SmemCtl);
@@ -579,7 +582,10 @@ static int score_max_tc(const uint16_t* q_bf16, int32_t M, int32_t Mpad, const u
   p.mask = mask; p.out_max = out_max; p.out_arg = out_arg; p.out_gap = out_gap; p.ld_out = ld_out;
   p.out_flags = out_flags; p.tau = tau; p.flag_words = (Nv + 31) / 32;
   p.flag_cnt = flag_cnt; p.flag_list = flag_list; p.flag_cap = flag_cap;
-  // videos (pairs) per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1
+  // videos (pairs) per work item: enough items for every worker (CTA or CTA pair) x several waves, >= 1.  Longer
+  // items (fewer reloads of the resident query tile) were tried — 24 / 32 / 40 / 51 / 64 videos, also a cost model that
+  // avoids a ragged last round: interleaved in one process they are all within 2 % of 16, and 64 is 5 % slower
+  // (profiles/r2_ab_gemm_items.md).
   const int num_q_tiles = Mpad / (kBlockM * cta);
   const int workers = sms / cta;
   int vc = 16;

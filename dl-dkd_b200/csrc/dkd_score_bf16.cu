@@ -48,21 +48,30 @@ constexpr float kNegHuge = -3.0e38f;
 // one 16-column chunk: r[0..15] raw fp32 bits, chunk id `cid`.  kTop2 = false (no gap / flag output requested: the frame
 // head) tracks the maximum only: LOP3 + FMNMX per element instead of LOP3 + 3 FMNMX — the epilogue, not the tensor
 // pipe, bounds the R = 128 problem.
-template <bool kHasMask, bool kTop2>
+__device__ __forceinline__ bool words_have_zero_byte(const uint4 mw) {
+  const uint32_t z = ((mw.x - 0x01010101u) & ~mw.x) | ((mw.y - 0x01010101u) & ~mw.y) |
+                     ((mw.z - 0x01010101u) & ~mw.z) | ((mw.w - 0x01010101u) & ~mw.w);
+  return (z & 0x80808080u) != 0;
+}
+// Does the 16-column chunk at mrow (16 mask bytes, 16-byte aligned because R % 16 == 0) hold a masked column?
+__device__ __forceinline__ bool chunk_has_masked(const uint8_t* mrow) {
+  return words_have_zero_byte(__ldg(reinterpret_cast<const uint4*>(mrow)));
+}
+// 16-byte read-only load that stays where it is written (volatile asm: issued here, consumed much later)
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint8_t* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
+// mrow != nullptr: the chunk has masked columns (their scores become the fill value); nullptr: no masked column —
+// the unmasked instruction stream.  The mask depends on (video, column) only, so it is uniform over the warp (lanes
+// are query rows) and the branch is divergence free.
+template <bool kTop2>
 __device__ __forceinline__ void top2_chunk(Top2& t, const uint32_t* r, int cid, const uint8_t* mrow) {
   const float before = t.best;
-  // The mask depends on (video, column) only, so it is uniform over the warp (lanes are query rows): one 16-byte
-  // load per chunk and a divergence-free branch.  Chunks without a masked column (every chunk of a full-length
-  // video) take the unmasked instruction stream; rows are 16-byte aligned because R % 16 == 0.
-  bool any_masked = false;
-  uint4 mw = make_uint4(0, 0, 0, 0);
-  if (kHasMask) {
-    mw = __ldg(reinterpret_cast<const uint4*>(mrow));
-    const uint32_t z = ((mw.x - 0x01010101u) & ~mw.x) | ((mw.y - 0x01010101u) & ~mw.y) |
-                       ((mw.z - 0x01010101u) & ~mw.z) | ((mw.w - 0x01010101u) & ~mw.w);
-    any_masked = (z & 0x80808080u) != 0;          // some byte of the 16 is zero
-  }
-  if (kHasMask && any_masked) {
+  if (mrow != nullptr) {
+    const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mrow));
     const uint32_t w[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -348,11 +357,24 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         // one whole video per warp: column half `half` of pair v is video 2 v + half
         const int rr = p.R >> 1;                    // rows per video
         const int nch = rr >> 4;                    // 16-column chunks per video (<= 8)
+        uint32_t mbits_next = 0;
         for (int v = v0; v < v1; ++v, ++tile_ctr) {
           const int vr = 2 * v + half;
           Top2 t2;
           t2.best = kNegHuge; t2.second = kNegHuge; t2.chunk = 0;
           const uint8_t* mvid = kHasMask ? p.mask + (int64_t)min(vr, p.nv_real - 1) * rr : nullptr;
+          // which of the video's chunks hold masked columns: lane c looks at chunk c, BEFORE the wait for the
+          // accumulator, so the load's latency hides behind it (one dependent mask load per chunk inside the tile
+          // made the epilogue, not the tensor pipe, pace the R = 128 problem)
+          uint32_t mbits = 0;
+          uint4 mw_next = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+          if (kHasMask) {
+            mbits = v == v0 ? __ballot_sync(0xffffffffu, lane < nch && chunk_has_masked(mvid + (lane << 4))) : mbits_next;
+            // the NEXT video's mask bytes are requested now and looked at after this tile: their latency overlaps
+            // the tile's TMEM loads instead of sitting in front of the next accumulator wait
+            if (v + 1 < v1 && lane < nch)
+              mw_next = ldg_nc_v4(p.mask + (int64_t)min(vr + 2, p.nv_real - 1) * rr + (lane << 4));
+          }
           const uint32_t as = tile_ctr & 1u;
           const uint32_t aphase = (tile_ctr >> 1) & 1u;
           mbar_wait(&ctl->tmem_full[as], aphase);
@@ -373,13 +395,14 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c = c0 + i;
-              if (c < nch) top2_chunk<kHasMask, kTop2>(t2, r + 16 * i, c, kHasMask ? mvid + (c << 4) : nullptr);
+              if (c < nch) top2_chunk<kTop2>(t2, r + 16 * i, c, (kHasMask && ((mbits >> c) & 1u)) ? mvid + (c << 4) : nullptr);
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
           if (vr < p.nv_real && m < p.M) emit_result(p, m, vr, t2.best, t2.second, t2.chunk);
+          if (kHasMask) mbits_next = __ballot_sync(0xffffffffu, words_have_zero_byte(mw_next));
         }
       } else {
       for (int v = v0; v < v1; ++v, ++vctr) {
@@ -406,7 +429,11 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const int c = c_lo + i;
-            if (c < c_hi) top2_chunk<kHasMask, kTop2>(t2, r + 16 * i, cid0 + c, kHasMask ? mvid + ((cid0 + c) << 4) : nullptr);
+            if (c < c_hi) {
+              const uint8_t* mrow = kHasMask ? mvid + ((cid0 + c) << 4) : nullptr;
+              if (kHasMask && !chunk_has_masked(mrow)) mrow = nullptr;
+              top2_chunk<kTop2>(t2, r + 16 * i, cid0 + c, mrow);
+            }
           }
           tc_fence_before();
           __syncwarp();

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="two_scale")
     ap.add_argument("--rounds", type=int, default=12)
+    ap.add_argument("--no-mask", action="store_true", help="frame shape: pass no mask (the unmasked kernel)")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     M, Nv, D = 10895, 2179, 384
@@ -52,7 +53,8 @@ def main():
             rc = lib.dkd_score_max_bf16_lists(P(q.data_ptr()), M, Mpad, P(x.data_ptr()), Nv, R, D, None, P(om.data_ptr()),
                                               P(oa.data_ptr()), Nv, 1e-3, P(cnt.data_ptr()), P(lst.data_ptr()), M, 0, P(st))
         else:
-            rc = lib.dkd_score_max_bf16(P(q.data_ptr()), M, Mpad, P(x.data_ptr()), Nv, R, D, P(mask.data_ptr()),
+            rc = lib.dkd_score_max_bf16(P(q.data_ptr()), M, Mpad, P(x.data_ptr()), Nv, R, D,
+                                        None if a.no_mask else P(mask.data_ptr()),
                                         P(om.data_ptr()), P(oa.data_ptr()), None, Nv, None, 0.0, P(st))
         assert rc == 0, rc
 

@@ -392,15 +392,19 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               else if (c < nch) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
             }
             tmem_ld_wait();
+            if (c0 + 4 >= nch) {
+              // the last columns of the tile are in registers: hand the accumulator back to the MMA warp BEFORE the
+              // max / argmax work on them (with two accumulators the tile period is (MMA + epilogue hold time) / 2)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c = c0 + i;
               if (c < nch) top2_chunk<kTop2>(t2, r + 16 * i, c, (kHasMask && ((mbits >> c) & 1u)) ? mvid + (c << 4) : nullptr);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
           if (vr < p.nv_real && m < p.M) emit_result(p, m, vr, t2.best, t2.second, t2.chunk);
           if (kHasMask) mbits_next = __ballot_sync(0xffffffffu, words_have_zero_byte(mw_next));
         }
@@ -426,6 +430,15 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             else if (c < c_hi) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
           }
           tmem_ld_wait();
+          // The tile's columns are in registers: hand the accumulator back to the MMA warp BEFORE the max / argmax work.
+          // With two accumulators the tile period is max(MMA, (MMA + epilogue hold time) / 2); holding the buffer
+          // through ~300 ALU instructions per warp made the epilogue, not the tensor pipe, pace the kernel.
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCta == 1) mbar_arrive(&ctl->tmem_empty[as]);
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
+          }
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const int c = c_lo + i;
@@ -434,12 +447,6 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               if (kHasMask && !chunk_has_masked(mrow)) mrow = nullptr;
               top2_chunk<kTop2>(t2, r + 16 * i, cid0 + c, mrow);
             }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kCta == 1) mbar_arrive(&ctl->tmem_empty[as]);
-            else mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[as]), 0));
           }
         }
         // merge the two column halves of this query row (named barrier per lane quarter, 64 threads)

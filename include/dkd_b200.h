@@ -128,9 +128,12 @@ int dkd_clip_score_f32(const float* qn, int32_t M, const float* clip_planes, con
  * bf16 tcgen05/TMEM scoring GEMM with fused max/argmax epilogue (the hot kernel).
  *   q_bf16 (Mpad, D) normalised queries, Mpad % 128 == 0, rows >= M zero;
  *   x_bf16 (Nv * R, D) normalised corpus rows; R % 16 == 0, D % 64 == 0, D <= 512;
- *   mask   (Nv, R) uint8 or NULL.
+ *   mask   (Nv, R) uint8 (non-zero = valid, method/model.py:444-445) or NULL; 16-byte aligned (DKD_ERR_ALIGN
+ *          otherwise): the kernel reads it 16 columns at a time.  A video with no valid row scores exactly
+ *          DKD_MASKED_SCORE with argmax 0 (torch.max: first index).
  * Outputs as dkd_score_max_f32 (dense only).  Replaces method/model.py:318-327 (R = L) and the
- * clip-scale contraction of SURVEY §8 N3 (R = P = 528).
+ * clip-scale contraction of SURVEY §8 N3 (R = P = 528).  Videos of R <= 128 rows (the reference's frame head) are
+ * scored two per N = 2 R MMA tile on CTA pairs.
  * TMA descriptors are encoded on the host per call (cuTensorMapEncodeTiled fetched through
  * cudaGetDriverEntryPoint) and passed as kernel parameters: no workspace.
  * out_gap (optional): best score minus the runner-up score of the same (query, video) — pairs whose

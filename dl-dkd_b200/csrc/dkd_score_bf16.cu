@@ -430,9 +430,10 @@ score_max_bf16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             else if (c < c_hi) tmem_ld16_issue(taddr + (uint32_t)(c << 4), r + 32 * i);
           }
           tmem_ld_wait();
-          // The tile's columns are in registers: hand the accumulator back to the MMA warp BEFORE the max / argmax work.
-          // With two accumulators the tile period is max(MMA, (MMA + epilogue hold time) / 2); holding the buffer
-          // through ~300 ALU instructions per warp made the epilogue, not the tensor pipe, pace the kernel.
+          // The tile's columns are in registers: hand the accumulator back to the MMA warp BEFORE the max / argmax work
+          // (with two accumulators the tile period is max(MMA, (MMA + epilogue hold time) / 2)).  Measured: 1-2 % back
+          // to back, nothing when the chip is cool — at N = 176 the kernel is bound by the board's power cap, not by
+          // this hold time (profiles/r2_ab_gemm_items.md); for the masked R = 128 pair tiles above it was the limiter.
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
